@@ -1,0 +1,61 @@
+"""Compiles the CUDA sources into cave_b200/_C/libcave_b200.so for sm_100a (in-tree, so the
+built library travels to the GPU box with the repo snapshot)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "_C")
+LIB = os.path.join(OUT_DIR, "libcave_b200.so")
+SOURCES = ["scan_kernel.cu", "solve_kernel.cu", "abi.cu"]
+HEADERS = ["ctx.cuh", "layout.cuh", "scan_kernel.cuh", "solve_kernel.cuh", "solver_core.cuh",
+           os.path.join("..", "..", "include", "cave_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def _nvcc() -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found; cannot build the CUDA library")
+    return nvcc
+
+
+def is_fresh() -> bool:
+    if not os.path.exists(LIB):
+        return False
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return all(os.path.getmtime(p) <= t for p in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and is_fresh():
+        return LIB
+    os.makedirs(OUT_DIR, exist_ok=True)
+    objs, logs = [], []
+    procs = []
+    for s in SOURCES:
+        obj = os.path.join(OUT_DIR, s.replace(".cu", ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", obj]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for s, pr in procs:
+        out, _ = pr.communicate()
+        logs.append(f"== {s}\n{out}")
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {s}:\n{out}")
+    with open(os.path.join(OUT_DIR, "ptxas.log"), "w") as f:
+        f.write("\n".join(logs))
+    if verbose:
+        print("\n".join(logs))
+    subprocess.check_call([_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force=True, verbose="-v" in sys.argv))

@@ -1,0 +1,185 @@
+// extern "C" entry points declared in include/cave_b200.h.  Plain pointers and sizes only; no
+// allocation, no synchronisation, no exceptions across the boundary.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+
+#include "../../include/cave_b200.h"
+#include "layout.cuh"
+#include "scan_kernel.cuh"
+#include "solve_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+const int64_t kMaxD = 12288;        // shared-memory bound of the scan ring / u16 column ids
+const int64_t kMaxM = 65535;        // u16 variable ids in the CSC
+const int64_t kMaxB = 0x7fffffff;
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached > 0) return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
+        cached = n;
+        return n;
+    }
+    (void)cudaGetLastError();
+    return 148;                     // B200; used only for sizing when no device is visible
+}
+
+int64_t solver_ctas(int64_t B) {
+    int64_t n = (int64_t)sm_count() * env_int("CAVE_SOLVE_CTAS_PER_SM", 1);
+    return B < n ? B : n;
+}
+
+int check_shape(int64_t B, int64_t m_max, int64_t d) {
+    if (B <= 0 || m_max <= 0 || d <= 0) return fail(CAVE_EINVAL, "B, m_max and d must be positive (got %lld, %lld, %lld)",
+                                                    (long long)B, (long long)m_max, (long long)d);
+    if (d > kMaxD) return fail(CAVE_ELIMIT, "d = %lld exceeds the supported maximum %lld", (long long)d, (long long)kMaxD);
+    if (m_max > kMaxM) return fail(CAVE_ELIMIT, "m_max = %lld exceeds the supported maximum %lld", (long long)m_max, (long long)kMaxM);
+    if (B > kMaxB) return fail(CAVE_ELIMIT, "B = %lld exceeds the supported maximum", (long long)B);
+    return CAVE_OK;
+}
+
+void resolve_caps(const cave_solver_opts* o, int64_t m_max, int64_t d, int64_t* cap_rows, int64_t* cap_nnz) {
+    int64_t r = (o && o->cap_rows > 0) ? o->cap_rows : m_max;
+    if (r > m_max) r = m_max;
+    int64_t z = (o && o->cap_nnz > 0) ? o->cap_nnz : r * d;
+    if (z > r * d) z = r * d;
+    *cap_rows = r; *cap_nnz = z;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cave_abi_version(void) { return CAVE_B200_ABI_VERSION; }
+
+const char* cave_last_error(void) { return g_err.c_str(); }
+
+int cave_get_limits(cave_limits* out) {
+    if (!out) return fail(CAVE_EINVAL, "out is null");
+    out->max_d = kMaxD; out->max_m = kMaxM; out->max_batch = kMaxB;
+    return CAVE_OK;
+}
+
+int cave_pack_bytes(int64_t B, int64_t m_max, int64_t d, size_t* out) {
+    if (!out) return fail(CAVE_EINVAL, "out is null");
+    if (int e = check_shape(B, m_max, d)) return e;
+    *out = cave::make_pack_layout(B, m_max, d).total;
+    return CAVE_OK;
+}
+
+int cave_scratch_bytes(int64_t B, int64_t m_max, int64_t d, int compute_dtype, const cave_solver_opts* opts, size_t* out) {
+    if (!out) return fail(CAVE_EINVAL, "out is null");
+    if (int e = check_shape(B, m_max, d)) return e;
+    if (compute_dtype != CAVE_F32 && compute_dtype != CAVE_F64) return fail(CAVE_EINVAL, "bad compute_dtype %d", compute_dtype);
+    int64_t cr, cz;
+    resolve_caps(opts, m_max, d, &cr, &cz);
+    *out = cave::make_scratch_layout(B, d, cr, cz, 8, solver_ctas(B)).total;
+    return CAVE_OK;
+}
+
+int cave_pack(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, int64_t d, void* pack, size_t pack_bytes,
+              void* stream) {
+    if (!A || !pack) return fail(CAVE_EINVAL, "A and pack must not be null");
+    if (int e = check_shape(B, m_max, d)) return e;
+    const cave::PackLayout L = cave::make_pack_layout(B, m_max, d);
+    if (pack_bytes < L.total) return fail(CAVE_ENOSPC, "pack buffer has %zu bytes, %zu needed", pack_bytes, L.total);
+    if (((uintptr_t)pack & 255) != 0) return fail(CAVE_EINVAL, "pack must be 256-byte aligned");
+    char* base = (char*)pack;
+    cave::ScanParams p;
+    memset(&p, 0, sizeof(p));
+    p.A = A; p.m_rows = m_rows; p.B = (int)B; p.m_max = (int)m_max; p.d = (int)d; p.dpad = L.dpad;
+    p.nvalid = (int*)(base + L.nvalid); p.navg = (int*)(base + L.navg); p.ngen = (int*)(base + L.ngen);
+    p.gennnz = (int*)(base + L.gennnz); p.nsingc = (int*)(base + L.nsingc);
+    p.gen = (int2*)(base + L.gen); p.ctype = (unsigned char*)(base + L.ctype); p.avg = (float*)(base + L.avg);
+    cudaError_t e = cave::launch_scan(p, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(CAVE_ECUDA, "scan kernel launch failed: %s", cudaGetErrorString(e));
+    return CAVE_OK;
+}
+
+int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pred, int64_t B, int64_t m_max, int64_t d,
+                          double sign, int mode, double inner_ratio, int reduction, int io_dtype, int compute_dtype,
+                          const cave_solver_opts* opts, void* loss, void* loss_i, void* grad, void* proj, void* rnorm,
+                          int32_t* status, int32_t* iters, void* pack, size_t pack_bytes, void* scratch,
+                          size_t scratch_bytes, void* stream) {
+    if (!A || !pred || !loss_i || !grad || !pack || !scratch) return fail(CAVE_EINVAL, "A, pred, loss_i, grad, pack, scratch must not be null");
+    if (int e = check_shape(B, m_max, d)) return e;
+    if (mode < CAVE_MODE_EXACT || mode > CAVE_MODE_HEURISTIC) return fail(CAVE_EINVAL, "bad mode %d", mode);
+    if (reduction < CAVE_REDUCE_MEAN || reduction > CAVE_REDUCE_NONE) return fail(CAVE_EINVAL, "bad reduction %d", reduction);
+    if ((io_dtype != CAVE_F32 && io_dtype != CAVE_F64) || (compute_dtype != CAVE_F32 && compute_dtype != CAVE_F64))
+        return fail(CAVE_EINVAL, "bad dtype (io %d, compute %d)", io_dtype, compute_dtype);
+    if (!(sign == 1.0 || sign == -1.0)) return fail(CAVE_EINVAL, "sign must be +1 or -1");
+    if (!(inner_ratio >= 0.0 && inner_ratio <= 1.0)) return fail(CAVE_EINVAL, "inner_ratio must be in [0, 1]");
+    if (reduction != CAVE_REDUCE_NONE && !loss) return fail(CAVE_EINVAL, "loss must not be null for mean/sum");
+    if (((uintptr_t)scratch & 255) != 0 || ((uintptr_t)pack & 255) != 0) return fail(CAVE_EINVAL, "pack and scratch must be 256-byte aligned");
+
+    const cave::PackLayout PL = cave::make_pack_layout(B, m_max, d);
+    if (pack_bytes < PL.total) return fail(CAVE_ENOSPC, "pack buffer has %zu bytes, %zu needed", pack_bytes, PL.total);
+    int64_t cr, cz;
+    resolve_caps(opts, m_max, d, &cr, &cz);
+    const size_t T = 8;   // state vectors are double in both modes; sized for the f64 factor
+    const int64_t n_ctas = solver_ctas(B);
+    const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, cr, cz, T, n_ctas);
+    if (scratch_bytes < SL.total) return fail(CAVE_ENOSPC, "scratch buffer has %zu bytes, %zu needed", scratch_bytes, SL.total);
+
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!(opts && opts->warm_pack)) {
+        if (int e = cave_pack(A, m_rows, B, m_max, d, pack, pack_bytes, stream)) return e;
+    }
+    char* pb = (char*)pack;
+    char* sb = (char*)scratch;
+    cudaError_t ce = cudaMemsetAsync(sb + SL.counter, 0, 256, st);
+    if (ce != cudaSuccess) return fail(CAVE_ECUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(ce));
+
+    cave::SolveParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.A = A; sp.pred = pred; sp.grad = grad; sp.proj = proj;
+    sp.B = (int)B; sp.m_max = (int)m_max; sp.d = (int)d; sp.dpad = PL.dpad;
+    sp.nvalid = (const int*)(pb + PL.nvalid); sp.ngen = (const int*)(pb + PL.ngen);
+    sp.gennnz = (const int*)(pb + PL.gennnz); sp.nsingc = (const int*)(pb + PL.nsingc);
+    sp.gen = (const int2*)(pb + PL.gen); sp.ctype = (const unsigned char*)(pb + PL.ctype); sp.avg = (const float*)(pb + PL.avg);
+    sp.counter = (int*)(sb + SL.counter); sp.loss64 = (double*)(sb + SL.loss64); sp.rnorm64 = (double*)(sb + SL.rnorm64);
+    sp.status = (int*)(sb + SL.status); sp.iters = (int*)(sb + SL.iters);
+    sp.slots = sb + SL.slots; sp.slot_bytes = SL.slot_bytes;
+    sp.smem_bytes = env_int("CAVE_SOLVE_SMEM", 220 * 1024);
+    sp.mode = mode; sp.inner_ratio = inner_ratio; sp.sign = sign;
+    sp.gscale = reduction == CAVE_REDUCE_MEAN ? 1.0 / (double)B : 1.0;
+    sp.max_iter = opts ? opts->max_iter : 0; sp.max_ls = opts ? opts->max_linesearch : 0; sp.tol = opts ? opts->tol : 0.0;
+    int threads = env_int("CAVE_SOLVE_THREADS", 256);
+    if (threads != 128 && threads != 256 && threads != 512) threads = 256;
+    ce = cave::launch_solve(sp, compute_dtype == CAVE_F32, io_dtype == CAVE_F32, (int)n_ctas, threads, st);
+    if (ce != cudaSuccess) return fail(CAVE_ECUDA, "solve kernel launch failed: %s", cudaGetErrorString(ce));
+
+    cave::FinalizeParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.B = (int)B; fp.reduction = reduction; fp.loss64 = sp.loss64; fp.rnorm64 = sp.rnorm64; fp.status = sp.status; fp.iters = sp.iters;
+    fp.loss = loss; fp.loss_i = loss_i; fp.rnorm = rnorm; fp.status_out = status; fp.iters_out = iters;
+    ce = cave::launch_finalize(fp, io_dtype == CAVE_F32, st);
+    if (ce != cudaSuccess) return fail(CAVE_ECUDA, "finalize kernel launch failed: %s", cudaGetErrorString(ce));
+    return CAVE_OK;
+}
+
+}  // extern "C"

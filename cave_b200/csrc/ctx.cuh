@@ -1,0 +1,126 @@
+// CTA execution context.  The solver core (solver_core.cuh) is written against this small
+// interface so that the same source compiles (a) as sm_100a device code, where a Ctx is one
+// CTA, and (b) with CAVE_HOST_SIM as plain single-threaded C++ (tid 0 of 1, warp width 1) for
+// CPU-side logic tests of the kernel (tests/hostsim).  The host build is test infrastructure
+// only; the product never loads it.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#ifdef CAVE_HOST_SIM
+#include <algorithm>
+#include <cstring>
+#define CAVE_DEV inline
+#define CAVE_RESTRICT
+namespace cave {
+struct Ctx {
+    static constexpr int WS = 1;
+    int tid = 0, nthr = 1, lane = 0, warp = 0, nwarp = 1;
+    void sync() {}
+    void syncwarp() {}
+    template <class T> T warp_sum(T v) { return v; }
+    template <class T> T warp_max(T v) { return v; }
+    template <class T> T block_sum(T v) { return v; }
+    template <class T> T block_max(T v) { return v; }
+    template <class T> T block_min(T v) { return v; }
+    // arg-max with smallest index on ties; idx < 0 means "no candidate"
+    template <class T> void block_argmax(T& v, int& idx) {}
+    template <class T> void block_argmin(T& v, int& idx) {}
+    unsigned ballot(bool p) { return p ? 1u : 0u; }
+    int lanes_below(unsigned) { return 0; }
+    int atomic_add(int* p, int v) { int o = *p; *p += v; return o; }
+    template <class T> T shfl(T v, int) { return v; }
+};
+CAVE_DEV float ld_stream(const float* p) { return *p; }
+}  // namespace cave
+#else
+#define CAVE_DEV __device__ __forceinline__
+#define CAVE_RESTRICT __restrict__
+namespace cave {
+struct Ctx {
+    static constexpr int WS = 32;
+    int tid, nthr, lane, warp, nwarp;
+    double* red;   // shared scratch: >= 2 * 32 doubles
+    __device__ Ctx(double* red_) : red(red_) {
+        tid = threadIdx.x; nthr = blockDim.x; lane = tid & 31; warp = tid >> 5; nwarp = nthr >> 5;
+    }
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ void syncwarp() { __syncwarp(); }
+    template <class T> __device__ __forceinline__ T shfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+    template <class T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    template <class T> __device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { T u = __shfl_xor_sync(0xffffffffu, v, o); v = u > v ? u : v; }
+        return v;
+    }
+    template <class T> __device__ __forceinline__ T warp_min(T v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { T u = __shfl_xor_sync(0xffffffffu, v, o); v = u < v ? u : v; }
+        return v;
+    }
+    // Block reductions: fixed order (lane tree, then warp 0 over the per-warp partials), result
+    // broadcast to every thread.  Two barriers each.
+    template <class T> __device__ T block_sum(T v) {
+        v = warp_sum(v);
+        sync();
+        if (lane == 0) red[warp] = (double)v;
+        sync();
+        double s = 0.0;
+        for (int w = 0; w < nwarp; ++w) s += red[w];
+        return (T)s;
+    }
+    template <class T> __device__ T block_max(T v) {
+        v = warp_max(v);
+        sync();
+        if (lane == 0) red[warp] = (double)v;
+        sync();
+        double s = red[0];
+        for (int w = 1; w < nwarp; ++w) s = red[w] > s ? red[w] : s;
+        return (T)s;
+    }
+    template <class T> __device__ T block_min(T v) {
+        v = warp_min(v);
+        sync();
+        if (lane == 0) red[warp] = (double)v;
+        sync();
+        double s = red[0];
+        for (int w = 1; w < nwarp; ++w) s = red[w] < s ? red[w] : s;
+        return (T)s;
+    }
+    template <class T> __device__ void block_argmax(T& v, int& idx) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            T u = __shfl_xor_sync(0xffffffffu, v, o);
+            int j = __shfl_xor_sync(0xffffffffu, idx, o);
+            bool take = (j >= 0) && (idx < 0 || u > v || (u == v && j < idx));
+            if (take) { v = u; idx = j; }
+        }
+        sync();
+        if (lane == 0) { red[warp] = (double)v; ((int*)(red + 32))[warp] = idx; }
+        sync();
+        double bv = 0.0; int bi = -1;
+        for (int w = 0; w < nwarp; ++w) {
+            double u = red[w]; int j = ((int*)(red + 32))[w];
+            if (j >= 0 && (bi < 0 || u > bv || (u == bv && j < bi))) { bv = u; bi = j; }
+        }
+        v = (T)bv; idx = bi;
+    }
+    template <class T> __device__ void block_argmin(T& v, int& idx) {
+        T nv = -v; block_argmax(nv, idx); v = -nv;
+    }
+    __device__ __forceinline__ unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+    __device__ __forceinline__ int lanes_below(unsigned mask) { return __popc(mask & ((1u << lane) - 1u)); }
+    __device__ __forceinline__ int atomic_add(int* p, int v) { return atomicAdd(p, v); }
+};
+// streaming global load that does not pollute L1 (rows of A are touched once per phase)
+CAVE_DEV float ld_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+}  // namespace cave
+#endif

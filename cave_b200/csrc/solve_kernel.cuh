@@ -1,0 +1,44 @@
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cave {
+
+struct SolveParams {
+    const float* A;
+    const void* pred;
+    void* grad;
+    void* proj;            // nullable
+    int B, m_max, d;
+    int64_t dpad;
+    // pack
+    const int *nvalid, *ngen, *gennnz, *nsingc;
+    const int2* gen;
+    const unsigned char* ctype;
+    const float* avg;
+    // scratch
+    int* counter;
+    double *loss64, *rnorm64;
+    int *status, *iters;
+    char* slots;
+    size_t slot_bytes;
+    int smem_bytes;
+    // epilogue / options
+    int mode;
+    double inner_ratio, sign, gscale;
+    int max_iter, max_ls;
+    double tol;
+};
+
+struct FinalizeParams {
+    int B, reduction;
+    const double *loss64, *rnorm64;
+    const int *status, *iters;
+    void *loss, *loss_i, *rnorm;
+    int *status_out, *iters_out;
+};
+
+cudaError_t launch_solve(const SolveParams& p, int compute_f32, int io_f32, int grid, int threads, cudaStream_t stream);
+cudaError_t launch_finalize(const FinalizeParams& p, int io_f32, cudaStream_t stream);
+
+}  // namespace cave

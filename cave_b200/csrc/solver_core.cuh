@@ -1,0 +1,745 @@
+// Per-instance cone projection solver + fused loss/backward epilogue, written against cave::Ctx
+// (one CTA per instance on the device; single thread under CAVE_HOST_SIM).
+//
+// Problem (reference src/cave.py:298-309): for the valid rows a_i of A,
+//     lambda* = argmin_{lambda >= 0} || sum_i lambda_i a_i - c ||^2 ,  p = sum_i lambda*_i a_i .
+// Rows with exactly one non-zero ("singleton" rows alpha*e_k; src/dataset.py:198-211 emits one per
+// variable) generate a product of 1-D cones, against which the distance is separable:
+//     psi_k(r) = r - proj_{I_k}(r),  I_k in { {0}, [0,inf), (-inf,0], R }   (ctype 0,1,2,3).
+// With B the remaining "general" rows the projection reduces exactly to
+//     min_{nu >= 0} f(nu) = 1/2 || psi(c - B^T nu) ||^2 ,    p = c - psi(c - B^T nu*)
+// a convex piecewise quadratic in dim(nu) = #general rows (~110 instead of ~1335 at TSP-50).
+//
+//  * Structured instances (some coordinate has a singleton row): projected semismooth Newton
+//    (Bertsekas' two-metric projection with the generalised Hessian B_F W B_F^T, W = diag(psi')),
+//    Armijo search along the projection arc.  Rows b_j = -b_i (an equality split into +- rows,
+//    src/dataset.py:182-184) are merged into one sign-free variable first.
+//  * Pure general instances (no singleton row at all, e.g. the dense rand/randn matrices of
+//    test/test_func.py:34-43): Lawson-Hanson active set in Gram form with an appended Cholesky
+//    row per pivot — the same algorithm family as scipy.optimize.nnls which the reference calls.
+//
+// Nothing here is first order: no step-size/momentum pair that could reproduce the FISTA
+// divergence documented in the reference README (README.md:40).
+#pragma once
+#include "ctx.cuh"
+
+namespace cave {
+
+#ifdef CAVE_HOST_SIM
+struct int2_ { int x, y; };
+typedef int2_ gen_t;
+struct float4_ { float x, y, z, w; };
+typedef float4_ f4_t;
+#else
+typedef int2 gen_t;
+typedef float4 f4_t;
+#endif
+
+enum { ST_CONVERGED = 0, ST_ITER_CAP = 1, ST_STALLED = 2, ST_NOSPACE = 3, ST_SKIPPED = 4, ST_PATH_LH = 0x100 };
+enum { MODE_EXACT = 0, MODE_INNER = 1, MODE_HEURISTIC = 2 };
+
+struct SolveOpts {
+    int max_iter;      // <= 0: default
+    int max_ls;
+    double tol;        // relative KKT tolerance
+};
+
+// Two-level bump allocator: shared memory first, the CTA's global scratch slot after that.
+struct Arena {
+    char* sm; size_t sm_cap, sm_off;
+    char* gl; size_t gl_cap, gl_off;
+    bool overflow;
+    CAVE_DEV void init(char* s, size_t sc, char* g, size_t gc) {
+        sm = s; sm_cap = sc; sm_off = 0; gl = g; gl_cap = gc; gl_off = 0; overflow = false;
+    }
+    template <class U> CAVE_DEV U* get(size_t n) {
+        size_t bytes = (n * sizeof(U) + 15) & ~(size_t)15;
+        if (sm_off + bytes <= sm_cap) { U* p = (U*)(sm + sm_off); sm_off += bytes; return p; }
+        if (gl_off + bytes <= gl_cap) { U* p = (U*)(gl + gl_off); gl_off += bytes; return p; }
+        overflow = true;
+        return (U*)gl;   // never dereferenced: callers check `overflow` before touching memory
+    }
+};
+
+template <class T> CAVE_DEV T psi(T r, int t) {
+    return t == 0 ? r : (t == 1 ? (r < (T)0 ? r : (T)0) : (t == 2 ? (r > (T)0 ? r : (T)0) : (T)0));
+}
+template <class T> CAVE_DEV bool psi_active(T r, int t) {
+    return t == 0 ? true : (t == 1 ? r < (T)0 : (t == 2 ? r > (T)0 : false));
+}
+template <class T> CAVE_DEV T cabs(T v) { return v < (T)0 ? -v : v; }
+template <class T> CAVE_DEV T eps_mach();
+template <> CAVE_DEV double eps_mach<double>() { return 2.220446049250313e-16; }
+template <> CAVE_DEV float eps_mach<float>() { return 1.1920929e-7f; }
+
+CAVE_DEV uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+
+// ------------------------------------------------------------------ dense Cholesky helpers
+// In-place right-looking Cholesky of the lower triangle of H (row-major, leading dim ld).  The
+// diagonal of L goes to diagL; H's own diagonal is left untouched.  Pivots are floored at
+// `floor_` so that semidefinite systems stay solvable (the Tikhonov term makes them consistent).
+template <class T>
+CAVE_DEV void chol_factor(Ctx& cx, T* H, int n, int ld, T* diagL, T floor_) {
+    for (int j = 0; j < n; ++j) {
+        cx.sync();
+        T piv = H[(size_t)j * ld + j];
+        T ljj = (T)sqrt((double)(piv > floor_ ? piv : floor_));
+        if (cx.tid == 0) diagL[j] = ljj;
+        T inv = (T)1 / ljj;
+        for (int i = j + 1 + cx.tid; i < n; i += cx.nthr) H[(size_t)i * ld + j] *= inv;
+        cx.sync();
+        for (int i = j + 1 + cx.warp; i < n; i += cx.nwarp) {
+            T lij = H[(size_t)i * ld + j];
+            for (int k = j + 1 + cx.lane; k <= i; k += Ctx::WS)
+                H[(size_t)i * ld + k] -= lij * H[(size_t)k * ld + j];
+        }
+    }
+    cx.sync();
+}
+
+// Forward substitution L y = x in place for rows [0, n) (warp 0 only; caller syncs afterwards).
+template <class T>
+CAVE_DEV void tri_forward_w0(Ctx& cx, const T* L, int n, int ld, const T* diagL, T* x) {
+    for (int j = 0; j < n; ++j) {
+        T yj = x[j] / diagL[j];
+        cx.syncwarp();
+        if (cx.lane == 0) x[j] = yj;
+        for (int i = j + 1 + cx.lane; i < n; i += Ctx::WS) x[i] -= L[(size_t)i * ld + j] * yj;
+        cx.syncwarp();
+    }
+}
+template <class T>
+CAVE_DEV void tri_backward_w0(Ctx& cx, const T* L, int n, int ld, const T* diagL, T* x) {
+    for (int j = n - 1; j >= 0; --j) {
+        T zj = x[j] / diagL[j];
+        cx.syncwarp();
+        if (cx.lane == 0) x[j] = zj;
+        for (int i = cx.lane; i < j; i += Ctx::WS) x[i] -= L[(size_t)j * ld + i] * zj;
+        cx.syncwarp();
+    }
+}
+template <class T>
+CAVE_DEV void chol_solve(Ctx& cx, const T* L, int n, int ld, const T* diagL, T* x) {
+    cx.sync();
+    if (cx.warp == 0) {
+        tri_forward_w0(cx, L, n, ld, diagL, x);
+        tri_backward_w0(cx, L, n, ld, diagL, x);
+    }
+    cx.sync();
+}
+
+// ------------------------------------------------------------------ instance description
+struct Instance {
+    const float* A;         // this instance's rows, [m_max, d] row-major (global)
+    const gen_t* gen;       // general rows: (row index, nnz), ascending row   (from the pack)
+    const uint8_t* ctype;   // [d] singleton cone type per coordinate            (from the pack)
+    const float* avg;       // [d] average unit normal (src/cave.py:222-228)     (from the pack)
+    int d, ngen, gen_nnz, nvalid, nsingc;
+};
+
+template <class T>
+struct Result {
+    T* r;          // [d] r = c - B^T nu at the solution; the residual is q = psi(r)
+    int iters;
+    int status;
+};
+
+// ------------------------------------------------------------------ Newton path
+template <class T, class TH>
+struct NewtonWork {
+    int d, mB, nv;
+    T *c, *r, *rt;
+    const uint8_t* ctype;
+    int* rptr; uint16_t* rcol; float* rval;      // CSR of the general rows
+    uint8_t* rtype;                               // 0 bounded, 1 free (merged +-), 2 dropped
+    int* grow;                                    // general row -> row index in A
+    int* vrow;                                    // variable -> CSR row
+    uint8_t* vfree;                               // variable is sign-free
+    int* cptr; uint16_t* crow; float* cval;      // CSC over variables
+    T *nu, *g, *dir, *nut;
+    int* flist;                                   // free-set variable ids
+    int* fpos;                                    // variable -> position in flist or -1
+    f4_t* scr4;                                   // [d] dense scratch, 4 rows at a time
+    TH* H; TH* diagL; TH* dF;                      // Hessian / Cholesky factor precision
+};
+
+template <class T, class TH>
+CAVE_DEV T nw_eval(Ctx& cx, const NewtonWork<T, TH>& W, const T* nu, T* rout) {
+    T acc = (T)0;
+    for (int k = cx.tid; k < W.d; k += cx.nthr) {
+        T rk = W.c[k];
+        for (int e = W.cptr[k]; e < W.cptr[k + 1]; ++e) rk -= (T)W.cval[e] * nu[W.crow[e]];
+        rout[k] = rk;
+        T q = psi(rk, (int)W.ctype[k]);
+        acc += q * q;
+    }
+    return (T)0.5 * cx.block_sum(acc);
+}
+
+template <class T, class TH>
+CAVE_DEV void nw_grad(Ctx& cx, const NewtonWork<T, TH>& W, const T* r, T* g) {
+    for (int v = cx.warp; v < W.nv; v += cx.nwarp) {
+        int row = W.vrow[v];
+        T acc = (T)0;
+        for (int e = W.rptr[row] + cx.lane; e < W.rptr[row + 1]; e += Ctx::WS) {
+            int k = W.rcol[e];
+            acc += (T)W.rval[e] * psi(r[k], (int)W.ctype[k]);
+        }
+        acc = cx.warp_sum(acc);
+        if (cx.lane == 0) g[v] = -acc;
+    }
+    cx.sync();
+}
+
+// H[b][a] = sum_k W_k B[f_b][k] B[f_a][k] for b >= a (lower triangle), four rows `a` per pass.
+template <class T, class TH>
+CAVE_DEV void nw_hessian(Ctx& cx, const NewtonWork<T, TH>& W, const T* r, int nf) {
+    for (int a0 = 0; a0 < nf; a0 += 4) {
+        int nb = nf - a0 < 4 ? nf - a0 : 4;
+        for (int rb = 0; rb < nb; ++rb) {
+            int row = W.vrow[W.flist[a0 + rb]];
+            for (int e = W.rptr[row] + cx.tid; e < W.rptr[row + 1]; e += cx.nthr) {
+                int k = W.rcol[e];
+                if (psi_active(r[k], (int)W.ctype[k])) ((float*)&W.scr4[k])[rb] = W.rval[e];
+            }
+        }
+        cx.sync();
+        for (int b = a0 + cx.warp; b < nf; b += cx.nwarp) {
+            int row = W.vrow[W.flist[b]];
+            TH s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            for (int e = W.rptr[row] + cx.lane; e < W.rptr[row + 1]; e += Ctx::WS) {
+                f4_t s = W.scr4[W.rcol[e]];
+                TH v = (TH)W.rval[e];
+                s0 += v * (TH)s.x; s1 += v * (TH)s.y; s2 += v * (TH)s.z; s3 += v * (TH)s.w;
+            }
+            s0 = cx.warp_sum(s0); s1 = cx.warp_sum(s1); s2 = cx.warp_sum(s2); s3 = cx.warp_sum(s3);
+            if (cx.lane == 0) {
+                TH* hb = W.H + (size_t)b * nf + a0;
+                if (a0 + 0 <= b) hb[0] = s0;
+                if (nb > 1 && a0 + 1 <= b) hb[1] = s1;
+                if (nb > 2 && a0 + 2 <= b) hb[2] = s2;
+                if (nb > 3 && a0 + 3 <= b) hb[3] = s3;
+            }
+        }
+        cx.sync();
+        for (int rb = 0; rb < nb; ++rb) {
+            int row = W.vrow[W.flist[a0 + rb]];
+            for (int e = W.rptr[row] + cx.tid; e < W.rptr[row + 1]; e += cx.nthr)
+                ((float*)&W.scr4[W.rcol[e]])[rb] = 0.f;
+        }
+        cx.sync();
+    }
+}
+
+// Build CSR of the general rows from A, merge +- pairs, build the variable list and the CSC.
+// Returns false (arena overflow) if the instance does not fit the scratch caps.
+template <class T, class TH>
+CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH>& W, T* maxrow_l1) {
+    const int d = in.d, mB = in.ngen;
+    W.d = d; W.mB = mB; W.ctype = in.ctype;
+    W.nu = ar.get<T>(mB + 1); W.g = ar.get<T>(mB + 1); W.dir = ar.get<T>(mB + 1); W.nut = ar.get<T>(mB + 1);
+    W.rptr = ar.get<int>(mB + 2);
+    W.grow = ar.get<int>(mB + 1);
+    W.rtype = ar.get<uint8_t>(mB + 1);
+    W.vrow = ar.get<int>(mB + 1);
+    W.vfree = ar.get<uint8_t>(mB + 1);
+    W.flist = ar.get<int>(mB + 1);
+    W.fpos = ar.get<int>(mB + 1);
+    uint64_t* key = ar.get<uint64_t>(mB + 1);
+    int* cand = ar.get<int>(mB + 1);
+    W.diagL = ar.get<TH>(mB + 1);
+    W.dF = ar.get<TH>(mB + 1);
+    W.scr4 = ar.get<f4_t>(d);
+    W.cptr = ar.get<int>(d + 2);
+    W.rcol = ar.get<uint16_t>(in.gen_nnz + 1);
+    W.rval = ar.get<float>(in.gen_nnz + 1);
+    if (ar.overflow) return false;
+
+    // row pointers (exclusive scan of the per-row counts the scan kernel stored)
+    for (int i = cx.tid; i < mB; i += cx.nthr) { gen_t g = in.gen[i]; W.grow[i] = g.x; W.rptr[i + 1] = g.y; }
+    for (int k = cx.tid; k < d; k += cx.nthr) { f4_t z; z.x = z.y = z.z = z.w = 0.f; W.scr4[k] = z; }
+    cx.sync();
+    if (cx.tid == 0) {
+        int acc = 0;
+        for (int i = 0; i < mB; ++i) { int n = W.rptr[i + 1]; W.rptr[i] = acc; acc += n; }
+        W.rptr[mB] = acc;
+    }
+    cx.sync();
+    // fill: one warp per row, ballot compaction keeps the columns sorted
+    T l1max = (T)0;
+    for (int i = cx.warp; i < mB; i += cx.nwarp) {
+        const float* row = in.A + (size_t)W.grow[i] * d;
+        int off = W.rptr[i];
+        uint64_t kacc = 0;
+        float l1 = 0.f;
+        for (int k0 = 0; k0 < d; k0 += Ctx::WS * 4) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int k = k0 + u * Ctx::WS + cx.lane;
+                v[u] = k < d ? ld_stream(row + k) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int k = k0 + u * Ctx::WS + cx.lane;
+                bool nz = v[u] != 0.f;
+                unsigned m = cx.ballot(nz);
+                if (nz) {
+                    int p = off + cx.lanes_below(m);
+                    W.rcol[p] = (uint16_t)k; W.rval[p] = v[u];
+                    union { float f; uint32_t u; } cv; cv.f = v[u];
+                    kacc += mix64(((uint64_t)k << 32) | (cv.u & 0x7fffffffu));
+                    l1 += v[u] < 0.f ? -v[u] : v[u];
+                }
+#ifdef CAVE_HOST_SIM
+                off += nz ? 1 : 0;
+#else
+                off += __popc(m);
+#endif
+            }
+        }
+        // wrapping 64-bit sum over lanes
+        uint32_t lo = (uint32_t)kacc, hi = (uint32_t)(kacc >> 32);
+#ifndef CAVE_HOST_SIM
+        for (int o = 16; o > 0; o >>= 1) {
+            uint64_t other = ((uint64_t)__shfl_xor_sync(0xffffffffu, hi, o) << 32) | __shfl_xor_sync(0xffffffffu, lo, o);
+            kacc += other; lo = (uint32_t)kacc; hi = (uint32_t)(kacc >> 32);
+        }
+#endif
+        l1 = cx.warp_sum(l1);
+        if (cx.lane == 0) key[i] = kacc;
+        if ((T)l1 > l1max) l1max = (T)l1;
+    }
+    *maxrow_l1 = cx.block_max(l1max);   // (barriers inside make the CSR visible)
+
+    // merge b_j = -b_i : cand[i] = smallest j != i with row_j == -row_i; merged iff mutual
+    for (int i = cx.tid; i < mB; i += cx.nthr) {
+        int c0 = -1;
+        int ni = W.rptr[i + 1] - W.rptr[i];
+        for (int j = 0; j < mB && c0 < 0; ++j) {
+            if (j == i || key[j] != key[i] || W.rptr[j + 1] - W.rptr[j] != ni) continue;
+            bool ok = true;
+            for (int e = 0; e < ni && ok; ++e)
+                ok = W.rcol[W.rptr[i] + e] == W.rcol[W.rptr[j] + e] && W.rval[W.rptr[i] + e] == -W.rval[W.rptr[j] + e];
+            if (ok) c0 = j;
+        }
+        cand[i] = c0;
+    }
+    cx.sync();
+    for (int i = cx.tid; i < mB; i += cx.nthr) {
+        int j = cand[i];
+        W.rtype[i] = (j >= 0 && cand[j] == i) ? (i < j ? 1 : 2) : 0;
+    }
+    cx.sync();
+    // variables = rows that were not dropped; count CSC entries
+    if (cx.tid == 0) {
+        int nv = 0, nz = 0;
+        for (int i = 0; i < mB; ++i)
+            if (W.rtype[i] != 2) { W.vrow[nv] = i; W.vfree[nv] = W.rtype[i] == 1; ++nv; nz += W.rptr[i + 1] - W.rptr[i]; }
+        W.flist[0] = nv; W.flist[1] = nz;   // broadcast through shared/global memory
+    }
+    cx.sync();
+    W.nv = W.flist[0];
+    int nnzc = W.flist[1];
+    cx.sync();
+    W.H = ar.get<TH>((size_t)W.nv * W.nv + 1);
+    W.crow = ar.get<uint16_t>(nnzc + 1);
+    W.cval = ar.get<float>(nnzc + 1);
+    if (ar.overflow) return false;
+    // CSC: count, scan, fill with a cursor, then order every column by variable id
+    int* cur = (int*)W.scr4;     // d ints, scratch is free here
+    for (int k = cx.tid; k <= d; k += cx.nthr) W.cptr[k] = 0;
+    cx.sync();
+    for (int v = cx.warp; v < W.nv; v += cx.nwarp) {
+        int row = W.vrow[v];
+        for (int e = W.rptr[row] + cx.lane; e < W.rptr[row + 1]; e += Ctx::WS) cx.atomic_add(&W.cptr[W.rcol[e] + 1], 1);
+    }
+    cx.sync();
+    if (cx.tid == 0) { for (int k = 0; k < d; ++k) W.cptr[k + 1] += W.cptr[k]; }
+    cx.sync();
+    for (int k = cx.tid; k < d; k += cx.nthr) cur[k] = W.cptr[k];
+    cx.sync();
+    for (int v = cx.warp; v < W.nv; v += cx.nwarp) {
+        int row = W.vrow[v];
+        for (int e = W.rptr[row] + cx.lane; e < W.rptr[row + 1]; e += Ctx::WS) {
+            int p = cx.atomic_add(&cur[W.rcol[e]], 1);
+            W.crow[p] = (uint16_t)v; W.cval[p] = W.rval[e];
+        }
+    }
+    cx.sync();
+    for (int k = cx.tid; k < d; k += cx.nthr) {      // insertion sort: deterministic summation order
+        int s = W.cptr[k], e = W.cptr[k + 1];
+        if (e - s <= 64)
+            for (int a = s + 1; a < e; ++a) {
+                uint16_t rr = W.crow[a]; float vv = W.cval[a]; int b = a - 1;
+                while (b >= s && W.crow[b] > rr) { W.crow[b + 1] = W.crow[b]; W.cval[b + 1] = W.cval[b]; --b; }
+                W.crow[b + 1] = rr; W.cval[b + 1] = vv;
+            }
+    }
+    cx.sync();
+    for (int k = cx.tid; k < d; k += cx.nthr) { f4_t z; z.x = z.y = z.z = z.w = 0.f; W.scr4[k] = z; }
+    cx.sync();
+    return true;
+}
+
+template <class T, class TH>
+CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, T* c, T* r, T* rt, T cnorm,
+                           const SolveOpts& opt, Result<T>& out) {
+    NewtonWork<T, TH> W;
+    W.c = c; W.r = r; W.rt = rt;
+    T l1max;
+    if (!nw_setup(cx, in, ar, W, &l1max)) { out.status = ST_NOSPACE; out.iters = 0; out.r = r; return; }
+    const int nv = W.nv;
+    const T scale = (l1max > (T)1 ? l1max : (T)1) * (cnorm > (T)1e-30 ? cnorm : (T)1e-30);
+    const T tol = (T)(opt.tol > 0 ? opt.tol : (sizeof(T) == 8 ? 1e-12 : 2e-6)) * scale;
+    const int max_iter = opt.max_iter > 0 ? opt.max_iter : 200;
+    const int max_ls = opt.max_ls > 0 ? opt.max_ls : 40;
+    const TH delta = sizeof(TH) == 8 ? (TH)1e-11 : (TH)2e-6;   // Tikhonov term, relative to max diag
+
+    for (int v = cx.tid; v < nv; v += cx.nthr) W.nu[v] = (T)0;
+    cx.sync();
+    T *nu = W.nu, *nut = W.nut, *rc = W.r, *rn = W.rt;
+    T f = nw_eval(cx, W, nu, rc);
+    int status = ST_ITER_CAP, it = 0;
+    for (; it < max_iter; ++it) {
+        nw_grad(cx, W, rc, W.g);
+        T res = (T)0;
+        for (int v = cx.tid; v < nv; v += cx.nthr) {
+            T t = nu[v] - W.g[v];
+            if (!W.vfree[v] && t < (T)0) t = (T)0;
+            T w = cabs(nu[v] - t);
+            res = w > res ? w : res;
+        }
+        res = cx.block_max(res);
+        if (!(res > tol)) { status = ST_CONVERGED; break; }
+        T epsb = res < (T)1e-3 ? res : (T)1e-3;
+        if (cx.tid == 0) {      // ordered free list (every variable that is not epsilon-binding)
+            int nf = 0;
+            for (int v = 0; v < nv; ++v) {
+                bool bind = !W.vfree[v] && nu[v] <= epsb && W.g[v] > (T)0;
+                W.fpos[v] = bind ? -1 : nf;
+                if (!bind) W.flist[nf++] = v;
+            }
+            W.fpos[nv] = nf;
+        }
+        cx.sync();
+        const int nf = W.fpos[nv];
+        if (nf > 0) {
+            nw_hessian(cx, W, rc, nf);
+            TH dmax = (TH)0;
+            for (int a = cx.tid; a < nf; a += cx.nthr) { TH h = W.H[(size_t)a * nf + a]; dmax = h > dmax ? h : dmax; }
+            dmax = cx.block_max(dmax);
+            if (!(dmax > (TH)0)) dmax = (TH)1;
+            for (int a = cx.tid; a < nf; a += cx.nthr) W.H[(size_t)a * nf + a] += delta * dmax;
+            chol_factor(cx, W.H, nf, nf, W.diagL, eps_mach<TH>() * dmax);
+        }
+        // direction: Newton on the free set (solved in place in dir[0..nf)), gradient on the binding set
+        TH* dF = W.dF;
+        for (int a = cx.tid; a < nf; a += cx.nthr) dF[a] = (TH)W.g[W.flist[a]];
+        if (nf > 0) chol_solve(cx, W.H, nf, nf, W.diagL, dF); else cx.sync();
+        for (int v = cx.tid; v < nv; v += cx.nthr) W.dir[v] = W.fpos[v] >= 0 ? (T)dF[W.fpos[v]] : W.g[v];
+        cx.sync();
+        // Armijo along the projection arc
+        T alpha = (T)1, ft = f;
+        bool ok = false;
+        for (int ls = 0; ls < max_ls; ++ls) {
+            T dec = (T)0;
+            for (int v = cx.tid; v < nv; v += cx.nthr) {
+                T t = nu[v] - alpha * W.dir[v];
+                if (!W.vfree[v] && t < (T)0) t = (T)0;
+                nut[v] = t;
+                dec += W.g[v] * (nu[v] - t);
+            }
+            dec = cx.block_sum(dec);
+            ft = nw_eval(cx, W, nut, rn);
+            if (ft <= f - (T)1e-4 * dec + (T)4 * eps_mach<T>() * f) { ok = true; break; }
+            alpha *= (T)0.5;
+        }
+        if (!ok) { status = ST_STALLED; break; }
+        T* t1 = nu; nu = nut; nut = t1;
+        T* t2 = rc; rc = rn; rn = t2;
+        f = ft;
+    }
+    out.r = rc; out.iters = it; out.status = status;
+}
+
+// ------------------------------------------------------------------ Lawson-Hanson path (dense rows)
+template <class T>
+CAVE_DEV T row_dot(Ctx& cx, const float* row, const T* x, int d) {   // one warp, result on all lanes
+    T acc = (T)0;
+    for (int k0 = 0; k0 < d; k0 += Ctx::WS * 4) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { int k = k0 + u * Ctx::WS + cx.lane; v[u] = k < d ? ld_stream(row + k) : 0.f; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { int k = k0 + u * Ctx::WS + cx.lane; if (k < d) acc += (T)v[u] * x[k]; }
+    }
+    return cx.warp_sum(acc);
+}
+
+template <class T, class TH>
+CAVE_DEV void lh_solve(Ctx& cx, const Instance& in, Arena& ar, T* c, T* r, T cnorm,
+                       const SolveOpts& opt, Result<T>& out) {
+    const int d = in.d, mB = in.ngen;
+    const int kmax = mB < d ? mB : d;
+    const int ld = kmax;
+    T* xP = ar.get<T>(kmax + 1); TH* s = ar.get<TH>(kmax + 1); T* bP = ar.get<T>(kmax + 1);
+    TH* tmp = ar.get<TH>(kmax + 2); TH* diagL = ar.get<TH>(kmax + 1);
+    int* P = ar.get<int>(kmax + 1); int* map = ar.get<int>(kmax + 2);
+    uint8_t* st = ar.get<uint8_t>(mB + 1);
+    int* grow = ar.get<int>(mB + 1);
+    T* rowv = ar.get<T>(d);                 // staged entering row
+    TH* L = ar.get<TH>((size_t)kmax * kmax + 1);
+    TH* Gp = ar.get<TH>((size_t)kmax * kmax + 1);
+    out.r = r; out.iters = 0;
+    if (ar.overflow) { out.status = ST_NOSPACE | ST_PATH_LH; return; }
+
+    for (int i = cx.tid; i < mB; i += cx.nthr) { st[i] = 0; grow[i] = in.gen[i].x; }
+    for (int k = cx.tid; k < d; k += cx.nthr) r[k] = c[k];
+    cx.sync();
+    // scale = max_i ||a_i||_1 * ||c||
+    T l1max = (T)0;
+    for (int i = cx.warp; i < mB; i += cx.nwarp) {
+        const float* row = in.A + (size_t)grow[i] * d;
+        T acc = (T)0;
+        for (int k = cx.lane; k < d; k += Ctx::WS) { float v = ld_stream(row + k); acc += (T)(v < 0.f ? -v : v); }
+        acc = cx.warp_sum(acc);
+        l1max = acc > l1max ? acc : l1max;
+    }
+    l1max = cx.block_max(l1max);
+    const T scale = (l1max > (T)1 ? l1max : (T)1) * (cnorm > (T)1e-30 ? cnorm : (T)1e-30);
+    const T tolw = (T)(opt.tol > 0 ? opt.tol : (sizeof(T) == 8 ? 1e-12 : 2e-6)) * scale;
+    const int cap = opt.max_iter > 0 ? opt.max_iter : 3 * mB + 10;
+    const TH dep_tol = sizeof(TH) == 8 ? (TH)1e-11 : (TH)1e-5;
+    int k = 0, iters = 0, status = ST_CONVERGED;
+
+    for (;;) {
+        // dual vector on the zero set: w_i = a_i . r ; pick the largest
+        T best = (T)0; int bi = -1;
+        for (int i = cx.warp; i < mB; i += cx.nwarp) {
+            if (st[i] != 0) continue;
+            T w = row_dot(cx, in.A + (size_t)grow[i] * d, r, d);
+            if (bi < 0 || w > best) { best = w; bi = i; }
+        }
+        cx.block_argmax(best, bi);
+        if (bi < 0 || !(best > tolw) || k >= kmax) break;
+        if (iters++ >= cap) { status = ST_ITER_CAP; break; }
+        const int j = bi;
+        const float* rowj = in.A + (size_t)grow[j] * d;
+        T gjj = (T)0, bj = (T)0;
+        for (int q = cx.tid; q < d; q += cx.nthr) { T v = (T)ld_stream(rowj + q); rowv[q] = v; gjj += v * v; bj += v * c[q]; }
+        gjj = cx.block_sum(gjj); bj = cx.block_sum(bj);
+        for (int idx = cx.warp; idx < k; idx += cx.nwarp) {
+            T h = row_dot(cx, in.A + (size_t)grow[P[idx]] * d, rowv, d);
+            if (cx.lane == 0) { Gp[(size_t)k * ld + idx] = (TH)h; tmp[idx] = (TH)h; }
+        }
+        cx.sync();
+        if (cx.warp == 0) {   // append a Cholesky row: L z = h, rho^2 = g_jj - z.z
+            tri_forward_w0(cx, L, k, ld, diagL, tmp);
+            TH zz = (TH)0;
+            for (int idx = cx.lane; idx < k; idx += Ctx::WS) zz += tmp[idx] * tmp[idx];
+            zz = cx.warp_sum(zz);
+            if (cx.lane == 0) tmp[k] = (TH)gjj - zz;
+        }
+        cx.sync();
+        TH rho2 = tmp[k];
+        cx.sync();
+        if (!(rho2 > dep_tol * (TH)gjj)) {     // numerically dependent on the passive set: skip for this round
+            if (cx.tid == 0) st[j] = 2;
+            cx.sync();
+            continue;
+        }
+        for (int idx = cx.tid; idx < k; idx += cx.nthr) L[(size_t)k * ld + idx] = tmp[idx];
+        if (cx.tid == 0) {
+            diagL[k] = (TH)sqrt((double)rho2); Gp[(size_t)k * ld + k] = (TH)gjj; L[(size_t)k * ld + k] = (TH)gjj;
+            P[k] = j; st[j] = 1; bP[k] = bj; xP[k] = (T)0;
+        }
+        cx.sync();
+        ++k;
+        for (int idx = cx.tid; idx < k; idx += cx.nthr) s[idx] = (TH)bP[idx];
+        chol_solve(cx, L, k, ld, diagL, s);
+        if (!(s[k - 1] > (TH)0)) {           // Lawson-Hanson step 6 safeguard
+            cx.sync();
+            --k;
+            if (cx.tid == 0) st[j] = 2;
+            cx.sync();
+            continue;
+        }
+        bool capped = false;
+        for (;;) {                          // inner loop: step back to feasibility, drop zeros
+            TH smin = (TH)1;
+            for (int idx = cx.tid; idx < k; idx += cx.nthr) smin = s[idx] < smin ? s[idx] : smin;
+            smin = cx.block_min(smin);
+            if (smin > (TH)0) break;
+            if (iters++ >= cap) { capped = true; break; }
+            T al = (T)2; int ai = -1;
+            for (int idx = cx.tid; idx < k; idx += cx.nthr)
+                if (!(s[idx] > (TH)0)) { T a = xP[idx] / (xP[idx] - (T)s[idx]); if (ai < 0 || a < al) { al = a; ai = idx; } }
+            cx.block_argmin(al, ai);
+            if (!(al >= (T)0)) al = (T)0;
+            T xmax = (T)0;
+            for (int idx = cx.tid; idx < k; idx += cx.nthr) {
+                T xn = xP[idx] + al * ((T)s[idx] - xP[idx]);
+                xP[idx] = xn;
+                xmax = xn > xmax ? xn : xmax;
+            }
+            xmax = cx.block_max(xmax);
+            if (cx.tid == 0) {              // compaction map (ordered)
+                int kn = 0;
+                for (int idx = 0; idx < k; ++idx) {
+                    bool rem = idx == ai || (!(s[idx] > (TH)0) && !(xP[idx] > (T)1e-14 * xmax));
+                    if (rem) st[P[idx]] = 0; else map[kn++] = idx;
+                }
+                map[kmax + 1] = kn;
+            }
+            cx.sync();
+            const int kn = map[kmax + 1];
+            // L <- compacted Gram (scratch), then Gp <- L, then factor L in place
+            for (int t = cx.tid; t < kn * kn; t += cx.nthr) {
+                int a = t / kn, b = t - a * kn;
+                if (b <= a) L[(size_t)a * ld + b] = Gp[(size_t)map[a] * ld + map[b]];
+            }
+            cx.sync();
+            for (int t = cx.tid; t < kn * kn; t += cx.nthr) {
+                int a = t / kn, b = t - a * kn;
+                if (b <= a) Gp[(size_t)a * ld + b] = L[(size_t)a * ld + b];
+            }
+            if (cx.tid == 0)
+                for (int a = 0; a < kn; ++a) { int o = map[a]; P[a] = P[o]; xP[a] = xP[o]; bP[a] = bP[o]; }
+            cx.sync();
+            k = kn;
+            TH dmax = (TH)0;
+            for (int a = cx.tid; a < k; a += cx.nthr) { TH h = Gp[(size_t)a * ld + a]; dmax = h > dmax ? h : dmax; }
+            dmax = cx.block_max(dmax);
+            chol_factor(cx, L, k, ld, diagL, eps_mach<TH>() * dmax);
+            for (int idx = cx.tid; idx < k; idx += cx.nthr) s[idx] = (TH)bP[idx];
+            chol_solve(cx, L, k, ld, diagL, s);
+            if (k == 0) break;
+        }
+        if (capped) { status = ST_ITER_CAP; break; }
+        for (int idx = cx.tid; idx < k; idx += cx.nthr) xP[idx] = (T)s[idx];
+        for (int i = cx.tid; i < mB; i += cx.nthr) if (st[i] == 2) st[i] = 0;
+        cx.sync();
+        for (int q = cx.tid; q < d; q += cx.nthr) {     // r = c - sum_P x_i a_i
+            T acc = c[q];
+            for (int idx = 0; idx < k; ++idx) acc -= xP[idx] * (T)in.A[(size_t)grow[P[idx]] * d + q];
+            r[q] = acc;
+        }
+        cx.sync();
+    }
+    if (sizeof(TH) < sizeof(T) && k > 0) {
+        // mixed precision: two rounds of iterative refinement of the passive-set least squares with
+        // the residual formed in T through A itself and the TH Cholesky factor as the solver
+        for (int round = 0; round < 2; ++round) {
+            for (int idx = cx.warp; idx < k; idx += cx.nwarp) {
+                T h = row_dot(cx, in.A + (size_t)grow[P[idx]] * d, r, d);
+                if (cx.lane == 0) s[idx] = (TH)h;
+            }
+            chol_solve(cx, L, k, ld, diagL, s);
+            for (int idx = cx.tid; idx < k; idx += cx.nthr) { T xn = xP[idx] + (T)s[idx]; xP[idx] = xn > (T)0 ? xn : (T)0; }
+            cx.sync();
+            for (int q = cx.tid; q < d; q += cx.nthr) {
+                T acc = c[q];
+                for (int idx = 0; idx < k; ++idx) acc -= xP[idx] * (T)in.A[(size_t)grow[P[idx]] * d + q];
+                r[q] = acc;
+            }
+            cx.sync();
+        }
+    }
+    out.iters = iters; out.status = status | ST_PATH_LH;
+}
+
+// ------------------------------------------------------------------ fused epilogue
+// target (src/cave.py:121-129, 197-219), loss = 1 - cos (src/cave.py:72), d loss / d pred.
+struct EpiParams {
+    int mode;
+    double inner_ratio, sign, gscale;   // gscale = 1/B for 'mean', 1 otherwise
+};
+
+template <class T, class TIO>
+CAVE_DEV void epilogue(Ctx& cx, const Instance& in, const EpiParams& ep, const T* c, const T* r,
+                       bool have_proj, bool empty_cone, T* tbuf,
+                       TIO* grad_out, TIO* proj_out, double* loss_out, double* rnorm_out) {
+    const int d = in.d;
+    double pp = 0.0, qq = 0.0, cc = 0.0;
+    for (int k = cx.tid; k < d; k += cx.nthr) {
+        double ck = (double)c[k];
+        double q = (have_proj && !empty_cone) ? (double)psi(r[k], (int)in.ctype[k]) : 0.0;
+        double p = ck - q;
+        pp += p * p; qq += q * q; cc += ck * ck;
+    }
+    pp = cx.block_sum(pp); qq = cx.block_sum(qq); cc = cx.block_sum(cc);
+    const double rnorm = sqrt(qq), pnorm = sqrt(pp), cnorm = sqrt(cc);
+    const double pden = pnorm > 1e-8 ? pnorm : 1e-8;
+    const double cden = cnorm > 1e-8 ? cnorm : 1e-8;
+    const double rr = ep.inner_ratio;
+    const bool push = ep.mode == MODE_INNER && !(rnorm < 1e-7);
+    double tt = 0.0, ct = 0.0;
+    for (int k = cx.tid; k < d; k += cx.nthr) {
+        double ck = (double)c[k], t;
+        if (ep.mode == MODE_HEURISTIC) {
+            t = (1.0 - rr) * (ck / cden) + rr * (double)in.avg[k];
+        } else {
+            double q = empty_cone ? 0.0 : (double)psi(r[k], (int)in.ctype[k]);
+            double ph = (ck - q) / pden;
+            t = push ? (1.0 - rr) * ph + rr * (double)in.avg[k] : ph;
+            if (proj_out) proj_out[k] = (TIO)(ck - q);
+        }
+        tbuf[k] = (T)t;
+        tt += t * t; ct += ck * t;
+    }
+    tt = cx.block_sum(tt); ct = cx.block_sum(ct);
+    const double tnorm = sqrt(tt);
+    const double tden = tnorm > 1e-8 ? tnorm : 1e-8;
+    const double cosv = ct / (cden * tden);
+    const double invc = cnorm > 0.0 ? 1.0 / cnorm : 0.0;
+    const double gs = ep.gscale * ep.sign;
+    for (int k = cx.tid; k < d; k += cx.nthr) {
+        double v = (double)tbuf[k] / tden;
+        double w = (double)c[k] * invc;
+        grad_out[k] = (TIO)(gs * (-(v - cosv * w) / cden));
+    }
+    if (cx.tid == 0) { *loss_out = 1.0 - cosv; *rnorm_out = (ep.mode == MODE_HEURISTIC) ? 0.0 : rnorm; }
+}
+
+// ------------------------------------------------------------------ one instance, start to finish
+template <class TH, class TIO>
+CAVE_DEV void solve_instance(Ctx& cx, const Instance& in, Arena& ar, const TIO* pred, const EpiParams& ep,
+                             const SolveOpts& opt, TIO* grad_out, TIO* proj_out,
+                             double* loss_out, double* rnorm_out, int* status_out, int* iters_out) {
+    typedef double T;      // state vectors are always double; TH is the Hessian / factor precision
+    const int d = in.d;
+    T* c = ar.get<T>(d); T* r = ar.get<T>(d); T* rt = ar.get<T>(d);
+    if (ar.overflow) {   // cannot even hold the cost vector: report, never a silent number
+        if (cx.tid == 0) { *loss_out = NAN; *rnorm_out = NAN; *status_out = ST_NOSPACE; *iters_out = 0; }
+        for (int k = cx.tid; k < d; k += cx.nthr) { grad_out[k] = (TIO)NAN; if (proj_out) proj_out[k] = (TIO)NAN; }
+        return;
+    }
+    T cc = (T)0;
+    for (int k = cx.tid; k < d; k += cx.nthr) { T v = (T)(ep.sign * (double)pred[k]); c[k] = v; r[k] = v; cc += v * v; }
+    cc = cx.block_sum(cc);
+    const T cnorm = (T)sqrt((double)cc);
+    Result<T> res; res.r = r; res.iters = 0; res.status = ST_SKIPPED;
+    const bool empty = in.nvalid == 0;
+    const bool solve = ep.mode != MODE_HEURISTIC && !empty;
+    if (solve && in.ngen > 0) {
+        if (in.nsingc == 0) lh_solve<T, TH>(cx, in, ar, c, r, cnorm, opt, res);
+        else newton_solve<T, TH>(cx, in, ar, c, r, rt, cnorm, opt, res);
+    } else if (solve) {
+        res.status = ST_CONVERGED;      // only singleton rows: closed form, r = c
+    }
+    cx.sync();
+    if ((res.status & 0xff) == ST_NOSPACE) {
+        if (cx.tid == 0) { *loss_out = NAN; *rnorm_out = NAN; *status_out = res.status; *iters_out = 0; }
+        for (int k = cx.tid; k < d; k += cx.nthr) { grad_out[k] = (TIO)NAN; if (proj_out) proj_out[k] = (TIO)NAN; }
+        return;
+    }
+    T* tbuf = (res.r == r) ? rt : r;
+    epilogue<T, TIO>(cx, in, ep, c, res.r, ep.mode != MODE_HEURISTIC, empty, tbuf, grad_out, proj_out, loss_out, rnorm_out);
+    if (cx.tid == 0) { *status_out = res.status; *iters_out = res.iters; }
+}
+
+}  // namespace cave

@@ -1,0 +1,159 @@
+"""
+``solver='cuda'`` backend for the CaVE cone projection — the counterpart of the reference's
+``src/qpsolver.py`` (which holds ``project_apgd``, src/qpsolver.py:11-63).
+
+``project_cuda`` has the calling convention of ``project_apgd`` and plugs into the batched early
+return of ``_batch_project`` (src/cave.py:242-244); unlike ``project_apgd`` its ``rnorm`` has the
+**nnls meaning** ``||proj - c||_2`` (src/cave.py:307), which is what the inner push-inside test
+``rnorm < 1e-7`` (src/cave.py:218) consumes.  ``cave_forward_backward`` is the fused variant
+(projection + target + loss + analytic backward in one pass).
+
+Host code here is plumbing only (argument checks, buffers, stream); all arithmetic runs in the
+hand-written sm_100a kernels behind the C ABI of include/cave_b200.h.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+_PRECISIONS = {"fp64": _lib.F64, "float64": _lib.F64, "double": _lib.F64,
+               "fp32": _lib.F32, "float32": _lib.F32, "single": _lib.F32}
+
+
+def _opts(max_iter=None, max_linesearch=None, tol=None, cap_rows=None, cap_nnz=None, warm=False) -> _lib.SolverOpts:
+    return _lib.SolverOpts(int(max_iter or 0), int(max_linesearch or 0), float(tol or 0.0),
+                           int(cap_rows or 0), int(cap_nnz or 0), int(bool(warm)), 0)
+
+
+def _device_of(t: torch.Tensor, device) -> torch.device:
+    if device is not None:
+        return torch.device(device)
+    if t.is_cuda:
+        return t.device
+    if not torch.cuda.is_available():
+        raise _lib.CaveLibraryError("solver='cuda' needs a CUDA device; there is no CPU fallback "
+                                    "(use the reference's solver='nnls' on the CPU)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_device(t: torch.Tensor, dev: torch.device, dtype=None) -> torch.Tensor:
+    if t.device != dev:
+        t = t.to(dev, non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+@dataclass
+class CavePack:
+    """Device-resident packed description of one ``tight_ctrs`` tensor (row classes, singleton cone
+    types, average normal).  A_i is constant across epochs, so a dataset can pack
+    once and pass ``pack=`` to skip the streaming pass over A on later calls."""
+    buf: torch.Tensor
+    shape: tuple
+    data_ptr: int
+
+
+def pack_constraints(tight_ctrs: torch.Tensor, m_rows: torch.Tensor | None = None) -> CavePack:
+    lib = _lib.load()
+    if not tight_ctrs.is_cuda:
+        raise ValueError("pack_constraints expects a CUDA tensor")
+    A = tight_ctrs.detach()
+    if A.dtype != torch.float32 or not A.is_contiguous():
+        raise ValueError("tight_ctrs must be contiguous float32 [B, m, d] (the collate_fn layout)")
+    B, m, d = A.shape
+    nbytes = ctypes.c_size_t()
+    _lib.check(lib.cave_pack_bytes(B, m, d, ctypes.byref(nbytes)))
+    buf = torch.empty(nbytes.value, dtype=torch.uint8, device=A.device)
+    with torch.cuda.device(A.device):
+        stream = torch.cuda.current_stream(A.device).cuda_stream
+        _lib.check(lib.cave_pack(_ptr(A), _ptr(m_rows), B, m, d, _ptr(buf), nbytes.value, ctypes.c_void_p(stream)))
+    return CavePack(buf, (B, m, d), A.data_ptr())
+
+
+def cave_forward_backward(pred_cost: torch.Tensor, tight_ctrs: torch.Tensor, sign: float, mode: int,
+                          inner_ratio: float = 0.2, reduction: str = "mean", precision: str = "fp64",
+                          want_proj: bool = False, want_status: bool = False, pack: CavePack | None = None,
+                          m_rows: torch.Tensor | None = None, device=None, max_iter=None, max_linesearch=None,
+                          tol=None, cap_rows=None, cap_nnz=None) -> dict:
+    """One call of the hot path through the C ABI.  Returns a dict with ``loss`` (scalar for
+    mean/sum, [B] for none), ``loss_i`` [B], ``grad`` [B, d] (= d loss / d pred_cost for an upstream
+    gradient of one), and optionally ``proj``, ``rnorm``, ``status``, ``iters`` — all on the
+    compute device, in ``pred_cost``'s dtype."""
+    lib = _lib.load()
+    if pred_cost.dim() != 2 or tight_ctrs.dim() != 3 or tight_ctrs.shape[0] != pred_cost.shape[0] \
+            or tight_ctrs.shape[2] != pred_cost.shape[1]:
+        raise ValueError(f"shape mismatch: pred_cost {tuple(pred_cost.shape)}, tight_ctrs {tuple(tight_ctrs.shape)}")
+    if reduction not in _lib.REDUCE:
+        raise ValueError(f"No reduction '{reduction}'.")
+    if precision not in _PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+    dev = _device_of(tight_ctrs if tight_ctrs.is_cuda else pred_cost, device)
+    io_dtype = torch.float64 if pred_cost.dtype == torch.float64 else torch.float32
+    pred = _to_device(pred_cost.detach(), dev, io_dtype)
+    A = _to_device(tight_ctrs.detach(), dev, torch.float32)
+    B, m, d = A.shape
+    if B == 0:
+        z = torch.zeros((), dtype=io_dtype, device=dev)
+        return dict(loss=z if reduction != "none" else torch.zeros(0, dtype=io_dtype, device=dev),
+                    loss_i=torch.zeros(0, dtype=io_dtype, device=dev), grad=torch.zeros_like(pred))
+    if m == 0:      # no rows at all: behave like all-padding (src/cave.py:304-305)
+        A = torch.zeros((B, 1, d), dtype=torch.float32, device=dev)
+        m = 1
+    compute = _PRECISIONS[precision]
+    opts = _opts(max_iter, max_linesearch, tol, cap_rows, cap_nnz, warm=pack is not None)
+    nb = ctypes.c_size_t()
+    if pack is not None:
+        if pack.shape != (B, m, d) or pack.buf.device != dev:
+            raise ValueError("pack does not belong to this tight_ctrs tensor")
+        pack_buf = pack.buf
+    else:
+        _lib.check(lib.cave_pack_bytes(B, m, d, ctypes.byref(nb)))
+        pack_buf = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+    _lib.check(lib.cave_scratch_bytes(B, m, d, compute, ctypes.byref(opts), ctypes.byref(nb)))
+    scratch = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+    loss = torch.empty((), dtype=io_dtype, device=dev)
+    loss_i = torch.empty(B, dtype=io_dtype, device=dev)
+    grad = torch.empty((B, d), dtype=io_dtype, device=dev)
+    proj = torch.empty((B, d), dtype=io_dtype, device=dev) if want_proj else None
+    rnorm = torch.empty(B, dtype=io_dtype, device=dev) if (want_proj or want_status) else None
+    status = torch.empty(B, dtype=torch.int32, device=dev) if want_status else None
+    iters = torch.empty(B, dtype=torch.int32, device=dev) if want_status else None
+    if m_rows is not None:
+        m_rows = _to_device(m_rows, dev, torch.int32)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.cave_forward_backward(
+            _ptr(A), _ptr(m_rows), _ptr(pred), B, m, d, float(sign), int(mode), float(inner_ratio),
+            _lib.REDUCE[reduction], _lib.F64 if io_dtype == torch.float64 else _lib.F32, compute,
+            ctypes.byref(opts), _ptr(loss), _ptr(loss_i), _ptr(grad), _ptr(proj), _ptr(rnorm), _ptr(status),
+            _ptr(iters), _ptr(pack_buf), pack_buf.numel(), _ptr(scratch), scratch.numel(), ctypes.c_void_p(stream)))
+    out = dict(loss=loss_i if reduction == "none" else loss, loss_i=loss_i, grad=grad)
+    if want_proj:
+        out["proj"], out["rnorm"] = proj, rnorm
+    if want_status:
+        out["status"], out["iters"], out["rnorm"] = status, iters, rnorm
+    return out
+
+
+def project_cuda(tight_ctrs: torch.Tensor, signed_cost: torch.Tensor, precision: str = "fp64",
+                 **solver_kwargs) -> tuple[torch.Tensor, torch.Tensor]:
+    """Batched projection of ``signed_cost`` onto cone{lam @ tight_ctrs[i] : lam >= 0}.
+
+    Drop-in for the batched branch of ``_batch_project`` (src/cave.py:242-244): returns
+    ``(proj [B, d], rnorm [B])`` on ``signed_cost``'s device and dtype (src/cave.py:240, 262-263),
+    ``rnorm = ||proj - c||_2`` as for ``_project_nnls`` (src/cave.py:307)."""
+    out = cave_forward_backward(signed_cost, tight_ctrs, sign=1.0, mode=_lib.MODE_EXACT, reduction="none",
+                                precision=precision, want_proj=True, **solver_kwargs)
+    proj, rnorm = out["proj"], out["rnorm"]
+    if proj.device != signed_cost.device:
+        proj, rnorm = proj.to(signed_cost.device), rnorm.to(signed_cost.device)
+    return proj.to(signed_cost.dtype), rnorm.to(signed_cost.dtype)

@@ -1,0 +1,127 @@
+/*
+ * cave_b200.h — C ABI of the B200-native CaVE cone-projection backend (solver='cuda').
+ *
+ * This is the drop-in boundary for ONE path of khalil-research/CaVE: the batched
+ * projection + push-inside + cosine loss + reduction + analytic backward that the
+ * reference computes in src/cave.py:55-73 (forward), :121-129 / :197-219
+ * (_get_projection), :222-228 (_average_ctrs), :231-264 (_batch_project) and
+ * :298-309 (_project_nnls -> scipy.optimize.nnls).  The reference has no FFI of its
+ * own (it is pure Python); the seam these entry points replace is the batched early
+ * return of _batch_project (src/cave.py:242-244, the `solver == "apgd"` hook), bound
+ * from Python with ctypes.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no C++/torch types; no exceptions.
+ *  - Every pointer is a DEVICE pointer unless stated.  The caller owns and allocates every
+ *    buffer (including pack and scratch); the library never allocates, frees or keeps a
+ *    pointer after the call returns.  Inputs are read-only.
+ *  - Calls only enqueue work on `stream` (a cudaStream_t passed as void*) and return
+ *    without synchronising.  Re-entrant across streams given distinct pack/scratch.
+ *  - Return value: 0 on success, a negative CAVE_E* code otherwise; cave_last_error()
+ *    returns a thread-local message for the last failure on the calling thread.
+ *  - `A` is the reference's collate_fn layout (src/dataset.py:133-144): float32
+ *    [B, m_max, d] row-major contiguous, all-zero rows are padding.  It may be over-read
+ *    by < 16 bytes on either side inside the enclosing 16-byte aligned granules.
+ */
+#ifndef CAVE_B200_H
+#define CAVE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAVE_B200_ABI_VERSION 1
+
+/* error codes */
+#define CAVE_OK 0
+#define CAVE_EINVAL (-1)    /* bad argument (null pointer, bad enum, size <= 0)          */
+#define CAVE_ELIMIT (-2)    /* shape outside the supported range (see cave_limits)         */
+#define CAVE_ENOSPC (-3)    /* pack / scratch buffer too small                             */
+#define CAVE_ECUDA (-4)     /* a CUDA runtime call failed (message in cave_last_error)     */
+
+/* mode: which target the loss is taken against */
+#define CAVE_MODE_EXACT 0      /* exactConeAlignedCosine            (src/cave.py:121-129)          */
+#define CAVE_MODE_INNER 1      /* innerConeAlignedCosine QP branch, nnls push-inside (:206-219)    */
+#define CAVE_MODE_HEURISTIC 2  /* innerConeAlignedCosine heuristic branch, no solve  (:201-204)    */
+
+/* reduction (optModule._reduce, called at src/cave.py:73) */
+#define CAVE_REDUCE_MEAN 0
+#define CAVE_REDUCE_SUM 1
+#define CAVE_REDUCE_NONE 2
+
+/* dtypes */
+#define CAVE_F32 0
+#define CAVE_F64 1
+
+/* per-instance status word written by the solver (never a silent NaN) */
+#define CAVE_ST_CONVERGED 0
+#define CAVE_ST_ITER_CAP 1      /* iteration cap hit; result is the best iterate           */
+#define CAVE_ST_STALLED 2       /* line search could not make progress                     */
+#define CAVE_ST_NOSPACE 3       /* instance exceeds scratch caps; outputs are NaN          */
+#define CAVE_ST_SKIPPED 4       /* heuristic mode or empty cone: no solve was needed       */
+#define CAVE_ST_PATH_LH 0x100   /* flag: solved by the Lawson-Hanson path (else Newton)    */
+
+typedef struct cave_solver_opts {
+    int32_t max_iter;        /* Newton iterations / LH pivots cap; <= 0 -> default (200 / 3*m) */
+    int32_t max_linesearch;  /* Armijo halvings cap; <= 0 -> default 40                        */
+    double tol;              /* KKT tolerance relative to max||a_i||_1 * ||c||; <= 0 -> default
+                                (1e-12 in f64 compute, 2e-6 in f32 compute)                    */
+    int64_t cap_rows;        /* scratch sizing: max general (non-singleton) rows per instance;
+                                <= 0 -> m_max                                                  */
+    int64_t cap_nnz;         /* scratch sizing: max non-zeros in those rows; <= 0 -> cap_rows*d */
+    int32_t warm_pack;       /* 1: `pack` already holds cave_pack() output for this A          */
+    int32_t reserved;
+} cave_solver_opts;
+
+typedef struct cave_limits {
+    int64_t max_d;       /* cost coefficients per instance             */
+    int64_t max_m;       /* padded rows per instance                   */
+    int64_t max_batch;   /* instances per call                         */
+} cave_limits;
+
+int cave_abi_version(void);
+const char* cave_last_error(void);
+int cave_get_limits(cave_limits* out);
+
+/* Bytes of the device-resident packed description of A (per-row classes, per-coordinate
+ * singleton cone types, average normal).  Replaces what `_average_ctrs` (src/cave.py:222-228)
+ * and the row mask of `_project_nnls` (src/cave.py:303) recompute on every call. */
+int cave_pack_bytes(int64_t B, int64_t m_max, int64_t d, size_t* out);
+
+/* Bytes of solver scratch (per-CTA sparse rows, Hessian, vectors, work counter). */
+int cave_scratch_bytes(int64_t B, int64_t m_max, int64_t d, int compute_dtype,
+                       const cave_solver_opts* opts, size_t* out);
+
+/* One streaming pass over A (HBM bound): classifies every row (padding / singleton +-e_k /
+ * general), accumulates the average unit normal, and writes the packed description.
+ * m_rows: optional int32[B] with the number of leading rows that can be non-zero per instance
+ * (rows >= m_rows[b] are not read); NULL -> all m_max rows are scanned. */
+int cave_pack(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, int64_t d,
+              void* pack, size_t pack_bytes, void* stream);
+
+/* The hot path.  pred: [B,d] predicted costs (io_dtype).  sign: -1 for EPO.MINIMIZE, +1 for
+ * EPO.MAXIMIZE (src/cave.py:62-68).  Outputs (io_dtype unless noted; any of proj, rnorm,
+ * status, iters, loss may be NULL):
+ *   loss    [1]   reduced loss for MEAN / SUM (ignored for NONE)
+ *   loss_i  [B]   per-instance 1 - cos(c, target)                        (required)
+ *   grad    [B,d] d(reduced loss)/d pred for an upstream gradient of 1   (required)
+ *   proj    [B,d] projection of c = sign*pred onto the cone  (what _batch_project returns)
+ *   rnorm   [B]   ||proj - c||_2                               (nnls meaning, src/cave.py:307)
+ *   status  [B]   int32 CAVE_ST_*;   iters [B] int32 solver iterations
+ * Unless opts->warm_pack is set, cave_pack() is run first on the same stream. */
+int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pred,
+                          int64_t B, int64_t m_max, int64_t d,
+                          double sign, int mode, double inner_ratio, int reduction,
+                          int io_dtype, int compute_dtype, const cave_solver_opts* opts,
+                          void* loss, void* loss_i, void* grad, void* proj, void* rnorm,
+                          int32_t* status, int32_t* iters,
+                          void* pack, size_t pack_bytes, void* scratch, size_t scratch_bytes,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAVE_B200_H */

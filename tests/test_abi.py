@@ -1,0 +1,59 @@
+"""The C-ABI shared library: loads, exports every symbol include/cave_b200.h declares, and its
+argument checking / sizing entry points behave (no compute calls here — those need a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from cave_b200 import _lib, build
+    build.build()
+    return _lib.load()
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "cave_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cave_[a-z_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = _declared_functions()
+    assert "cave_forward_backward" in names and "cave_pack" in names and len(names) >= 7
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/cave_b200.h but not exported"
+    from cave_b200 import _lib
+    assert sorted(_lib.EXPORTS) == names
+
+
+def test_version_limits_and_sizes(lib):
+    from cave_b200 import _lib
+    assert lib.cave_abi_version() == 1
+    lim = _lib.Limits()
+    assert lib.cave_get_limits(ctypes.byref(lim)) == 0
+    assert lim.max_d >= 4950 and lim.max_m >= 5200
+    n = ctypes.c_size_t()
+    assert lib.cave_pack_bytes(4096, 1337, 1225, ctypes.byref(n)) == 0
+    assert 4096 * 1337 * 8 < n.value < 4096 * 1337 * 1225 * 4 // 100      # ~1% of dense A
+    opts = _lib.SolverOpts(0, 0, 0.0, 128, 20000, 0, 0)
+    assert lib.cave_scratch_bytes(4096, 1337, 1225, _lib.F64, ctypes.byref(opts), ctypes.byref(n)) == 0
+    assert n.value > 0
+    small = n.value
+    assert lib.cave_scratch_bytes(4096, 1337, 1225, _lib.F64, None, ctypes.byref(n)) == 0
+    assert n.value > small
+
+
+def test_argument_errors_are_codes_with_messages(lib):
+    n = ctypes.c_size_t()
+    assert lib.cave_pack_bytes(0, 10, 10, ctypes.byref(n)) == -1
+    assert b"positive" in lib.cave_last_error()
+    assert lib.cave_pack_bytes(8, 10, 10 ** 6, ctypes.byref(n)) == -2
+    assert b"exceeds" in lib.cave_last_error()
+    assert lib.cave_pack(None, None, 8, 10, 10, None, 0, None) == -1
+    assert lib.cave_forward_backward(None, None, None, 8, 10, 10, -1.0, 0, 0.2, 0, 0, 1, None, None, None, None, None,
+                                     None, None, None, None, 0, None, 0, None) == -1

@@ -26,9 +26,14 @@ struct Ctx {
     // arg-max with smallest index on ties; idx < 0 means "no candidate"
     template <class T> void block_argmax(T& v, int& idx) {}
     template <class T> void block_argmin(T& v, int& idx) {}
+    template <class T> void block_sum2(T&, T&) {}
+    template <class T> void block_max2(T&, T&) {}
+    uint64_t warp_sum_u64(uint64_t v) { return v; }
     unsigned ballot(bool p) { return p ? 1u : 0u; }
     int lanes_below(unsigned) { return 0; }
+    int popc(unsigned m) { return (int)(m & 1u); }
     int atomic_add(int* p, int v) { int o = *p; *p += v; return o; }
+    template <class T> void atomic_addf(T* p, T v) { *p += v; }
     template <class T> T shfl(T v, int) { return v; }
 };
 CAVE_DEV float ld_stream(const float* p) { return *p; }
@@ -112,6 +117,31 @@ struct Ctx {
     template <class T> __device__ void block_argmin(T& v, int& idx) {
         T nv = -v; block_argmax(nv, idx); v = -nv;
     }
+    template <class T> __device__ void block_sum2(T& a, T& b) {
+        a = warp_sum(a); b = warp_sum(b);
+        sync();
+        if (lane == 0) { red[warp] = (double)a; red[32 + warp] = (double)b; }
+        sync();
+        double sa = 0.0, sb = 0.0;
+        for (int w = 0; w < nwarp; ++w) { sa += red[w]; sb += red[32 + w]; }
+        a = (T)sa; b = (T)sb;
+    }
+    template <class T> __device__ void block_max2(T& a, T& b) {
+        a = warp_max(a); b = warp_max(b);
+        sync();
+        if (lane == 0) { red[warp] = (double)a; red[32 + warp] = (double)b; }
+        sync();
+        double sa = red[0], sb = red[32];
+        for (int w = 1; w < nwarp; ++w) { sa = red[w] > sa ? red[w] : sa; sb = red[32 + w] > sb ? red[32 + w] : sb; }
+        a = (T)sa; b = (T)sb;
+    }
+    __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    __device__ __forceinline__ int popc(unsigned m) { return __popc(m); }
+    template <class T> __device__ __forceinline__ void atomic_addf(T* p, T v) { atomicAdd(p, v); }
     __device__ __forceinline__ unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
     __device__ __forceinline__ int lanes_below(unsigned mask) { return __popc(mask & ((1u << lane) - 1u)); }
     __device__ __forceinline__ int atomic_add(int* p, int v) { return atomicAdd(p, v); }

@@ -22,10 +22,20 @@ CAVE_HD size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 //   gen[B, m_max]   (row index, nnz) of every general row, ascending
 //   ctype[B, dpad]  per coordinate: bit0 = a row +a*e_k exists, bit1 = a row -a*e_k exists
 //   avg[B, dpad]    float32 average unit normal     (src/cave.py:222-228)
+//   csrok[B], maxl1[B], maxl2[B]   packed-CSR complete flag; max ||a||_1, max ||a||_2^2 over general rows
+//   ghash[B, m_max]   per general row: order-free 64-bit hashes of the row and of its negation
+//   csr_col/val[B, cap_nnz]   the general rows' non-zeros, row after row, columns ascending
 struct PackLayout {
-    size_t nvalid, navg, ngen, gennnz, nsingc, gen, ctype, avg, total;
-    int64_t dpad;
+    size_t nvalid, navg, ngen, gennnz, nsingc, gen, ctype, avg, csrok, maxl1, maxl2, ghash, csr_col, csr_val, total;
+    int64_t dpad, cap_nnz;
 };
+
+// per-instance capacity of the packed CSR: every shipped model (TSP/VRP/SP) fits; instances that do
+// not (dense general rows) are flagged and the solver reads their rows from A instead
+CAVE_HD int64_t pack_cap_nnz(int64_t m_max, int64_t d) {
+    int64_t full = m_max * d, c = 16 * d + 4096;
+    return (c < full ? c : full + 1) / 8 * 8 + 8;
+}
 
 CAVE_HD PackLayout make_pack_layout(int64_t B, int64_t m_max, int64_t d) {
     PackLayout L;
@@ -39,6 +49,13 @@ CAVE_HD PackLayout make_pack_layout(int64_t B, int64_t m_max, int64_t d) {
     L.gen = o;    o = align_up(o + (size_t)B * (size_t)m_max * 8, 256);
     L.ctype = o;  o = align_up(o + (size_t)B * (size_t)L.dpad, 256);
     L.avg = o;    o = align_up(o + (size_t)B * (size_t)L.dpad * 4, 256);
+    L.cap_nnz = pack_cap_nnz(m_max, d);
+    L.csrok = o;  o = align_up(o + (size_t)B * 4, 256);
+    L.maxl1 = o;  o = align_up(o + (size_t)B * 4, 256);
+    L.maxl2 = o;  o = align_up(o + (size_t)B * 4, 256);
+    L.ghash = o;  o = align_up(o + (size_t)B * (size_t)m_max * 16, 256);
+    L.csr_col = o; o = align_up(o + (size_t)B * (size_t)L.cap_nnz * 2, 256);
+    L.csr_val = o; o = align_up(o + (size_t)B * (size_t)L.cap_nnz * 4, 256);
     L.total = o;
     return L;
 }
@@ -52,8 +69,8 @@ struct ScratchLayout {
 CAVE_HD size_t solver_slot_bytes(int64_t d, int64_t cap_rows, int64_t cap_nnz, size_t T) {
     const size_t r = (size_t)cap_rows + 2, dd = (size_t)d + 2;
     // Newton path (upper bound over every Arena::get in nw_setup / newton_solve)
-    size_t nw = 3 * dd * T + 16 * dd + 4 * dd + r * (5 * T + 4 + 4 + 1 + 4 + 1 + 4 + 4 + 8 + 4)
-              + (size_t)(cap_nnz + 2) * 12 + r * r * T;
+    size_t nw = 3 * dd * T + 4 * dd + 4 * dd + r * (6 * T + 4 + 4 + 1 + 4 + 1 + 4 + 4 + 8 + 4)
+              + (size_t)(cap_nnz + 2) * 12 + r * r * T + (r + 1) * (r + 2) * T;
     // Lawson-Hanson path
     const size_t k = (cap_rows < d ? (size_t)cap_rows : (size_t)d) + 2;
     size_t lh = 3 * dd * T + dd * T + k * (5 * T + 8) + r * 5 + 2 * k * k * T;

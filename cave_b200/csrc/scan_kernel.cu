@@ -2,10 +2,14 @@
 //
 // One CTA per instance.  Row tiles are brought into a shared-memory ring with 1-D TMA bulk
 // copies (cp.async.bulk ... mbarrier::complete_tx) issued by one thread; eight warps consume:
-//   phase A  warp per row : sum|a|, sum a^2, non-zero count, position/sign of a lone non-zero
-//   phase B  one thread   : ordered bookkeeping (row classes, general-row list, singleton
-//                           cone types / +-1 contributions to the average)
-//            all threads  : column-parallel accumulation of a/||a|| over the general rows
+//   phase A  warp per row : aligned 128-bit shared loads; a warp-uniform "all four lanes' words
+//                           are zero" test skips the arithmetic for the (dominant) zero words,
+//                           so sparse rows cost ~2 instructions per element.  Per row: non-zero
+//                           count, and for rows that need them sum|a|, sum a^2, two order-free
+//                           64-bit row hashes (for +-row matching in the solver).
+//   phase B  one thread   : ordered bookkeeping of singleton rows (cone types, +-1 average terms)
+//            all threads  : column-parallel accumulation of a/||a|| over the general rows,
+//            warp per row : compaction of each general row into the packed CSR of the instance
 // Everything `_average_ctrs` (src/cave.py:222-228) and the row mask of `_project_nnls`
 // (src/cave.py:303) recompute on the host for every call is produced here in one read of A.
 // All accumulation orders are fixed, so the pack is bit-reproducible run to run.
@@ -42,6 +46,21 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                  : "memory");
 }
 
+__device__ __forceinline__ uint64_t mix64d(uint64_t x) {      // same mixer as solver_core.cuh
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+
+struct RowAcc {
+    float l1, l2, lv;
+    int lk, n;
+    __device__ __forceinline__ void add(float v, int k) {
+        l1 += fabsf(v);
+        l2 = fmaf(v, v, l2);
+        lk = k; lv = v; ++n;
+    }
+};
+
 template <int NT>
 __global__ void __launch_bounds__(NT) scan_kernel(ScanParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -53,15 +72,15 @@ __global__ void __launch_bounds__(NT) scan_kernel(ScanParams p) {
     unsigned char* ring = smem;
     float* avg_gen = (float*)(smem + (size_t)S * p.stage_stride);
     int* sing = (int*)(avg_gen + d);
-    float* r_l1 = (float*)(sing + d);
-    float* r_l2 = r_l1 + R;
-    float* r_inv = r_l2 + R;
+    uint64_t* full = (uint64_t*)align_up((size_t)(sing + d), 8);
+    float* r_l1 = (float*)(full + S);
+    float* r_nrm = r_l1 + R;
+    float* r_inv = r_nrm + R;
     float* r_val = r_inv + R;
     int* r_cnt = (int*)(r_val + R);
     int* r_k = r_cnt + R;
-    int* s_cnt = r_k + R;                                   // [8] nvalid, navg, ngen, gennnz, nsingc
-    uint64_t* full = (uint64_t*)align_up((size_t)(s_cnt + 8), 8);
-    unsigned char* ctype = (unsigned char*)(full + S);      // [dpad]
+    int* s_cnt = r_k + R;                                   // [8]
+    unsigned char* ctype = (unsigned char*)align_up((size_t)(s_cnt + 8), 16);   // [dpad]
 
     const int m_b = p.m_rows ? min(max(p.m_rows[b], 0), p.m_max) : p.m_max;
     const int ntiles = (m_b + R - 1) / R;
@@ -89,73 +108,161 @@ __global__ void __launch_bounds__(NT) scan_kernel(ScanParams p) {
     if (tid == 0)
         for (int t = 0; t < S && t < ntiles; ++t) issue(t);
 
-    // bookkeeper's private counters (thread NT-1)
-    int c_nvalid = 0, c_navg = 0, c_ngen = 0, c_gennnz = 0;
+    // running totals, replicated in every thread (identical arithmetic everywhere)
+    int t_ngen = 0, t_gennnz = 0;
+    float t_l1max = 0.f, t_l2max = 0.f;
+    // bookkeeper-only counters (thread NT-1)
+    int c_nvalid = 0, c_navg = 0;
+    int overflow = 0;
     int2* gen_out = p.gen + (size_t)b * p.m_max;
+    ulonglong2* hash_out = p.ghash + (size_t)b * p.m_max;
+    uint16_t* col_out = p.csr_col + (size_t)b * p.cap_nnz;
+    float* val_out = p.csr_val + (size_t)b * p.cap_nnz;
 
     for (int t = 0; t < ntiles; ++t) {
         const int s = t % S;
         const int rows = min(R, m_b - t * R);
         const uintptr_t a = (uintptr_t)(A_b + (size_t)t * R * d);
         const int shift = (int)((a & 15) >> 2);
-        const float* tile = (const float*)(ring + (size_t)s * p.stage_stride) + shift;
+        const float* base = (const float*)(ring + (size_t)s * p.stage_stride);   // 16-byte aligned
+        const float* tile = base + shift;
         mbar_wait(full + s, (uint32_t)((t / S) & 1));
 
         // ---- phase A: per-row statistics, one warp per row
         for (int rr = warp; rr < rows; rr += NW) {
-            const float* row = tile + (size_t)rr * d;
-            float l1 = 0.f, l2 = 0.f, lv = 0.f;
-            int cnt = 0, lk = -1;
-            for (int k = lane; k < d; k += 32) {
-                float v = row[k];
-                l1 += fabsf(v);
-                l2 = fmaf(v, v, l2);
-                if (v != 0.f) { ++cnt; lk = k; lv = v; }
+            const int e0 = shift + rr * d, e1 = e0 + d;         // element range in `base` coordinates
+            const int q0 = (e0 + 3) >> 2, q1 = e1 >> 2;         // whole float4 words inside the row
+            RowAcc acc; acc.l1 = 0.f; acc.l2 = 0.f; acc.lv = 0.f; acc.lk = -1; acc.n = 0;
+            int cnt = 0;
+            if (q0 <= q1) {
+                if (lane < 4) {                                  // ragged head and tail (< 4 elements each)
+                    const int kh = e0 + lane;
+                    if (kh < (q0 << 2) && kh < e1) { float v = base[kh]; if (v != 0.f) acc.add(v, kh - e0); }
+                    const int kt = (q1 << 2) + lane;
+                    if (kt >= (q0 << 2) && kt < e1) { float v = base[kt]; if (v != 0.f) acc.add(v, kt - e0); }
+                }
+                const float4* b4 = (const float4*)base;
+                for (int q = q0 + lane; q < q1 + lane; q += 32) {       // uniform trip count
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (q < q1) v = b4[q];
+                    const uint32_t any = (__float_as_uint(v.x) | __float_as_uint(v.y) | __float_as_uint(v.z) | __float_as_uint(v.w)) << 1;
+                    if (__ballot_sync(0xffffffffu, any != 0u) == 0u) continue;      // all 128 words are zero
+                    if (any != 0u) {
+                        const int k = (q << 2) - e0;
+                        if (v.x != 0.f) acc.add(v.x, k);
+                        if (v.y != 0.f) acc.add(v.y, k + 1);
+                        if (v.z != 0.f) acc.add(v.z, k + 2);
+                        if (v.w != 0.f) acc.add(v.w, k + 3);
+                    }
+                }
+            } else {                                             // row shorter than one aligned word
+                for (int k = e0 + lane; k < e1; k += 32) { float v = base[k]; if (v != 0.f) acc.add(v, k - e0); }
             }
+            // exact non-zero count of the row (lanes that saw nothing are skipped with one ballot)
+            const unsigned sawm = __ballot_sync(0xffffffffu, acc.n > 0);
+            if (sawm) {
+                if ((sawm & (sawm - 1)) == 0u) {
+                    cnt = __shfl_sync(0xffffffffu, acc.n, __ffs(sawm) - 1);
+                } else {
+                    cnt = acc.n;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                l1 += __shfl_xor_sync(0xffffffffu, l1, o);
-                l2 += __shfl_xor_sync(0xffffffffu, l2, o);
-                cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                }
             }
-            int lkmax = lk;
+            float l1 = 0.f, nrm = 0.f, v1 = 0.f;
+            int k1 = -1;
+            if (cnt == 1) {
+                const int src = __ffs(sawm) - 1;
+                k1 = __shfl_sync(0xffffffffu, acc.lk, src);
+                v1 = __shfl_sync(0xffffffffu, acc.lv, src);
+                l1 = fabsf(v1); nrm = sqrtf(v1 * v1);
+            } else if (cnt >= 2) {
+                float a1 = acc.l1, a2 = acc.l2;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) lkmax = max(lkmax, __shfl_xor_sync(0xffffffffu, lkmax, o));
-            unsigned owner = __ballot_sync(0xffffffffu, lk == lkmax && lk >= 0);
-            float v1 = __shfl_sync(0xffffffffu, lv, owner ? (__ffs(owner) - 1) : 0);
+                for (int o = 16; o > 0; o >>= 1) {
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+                }
+                l1 = a1; nrm = sqrtf(a2);
+            }
             if (lane == 0) {
-                float nrm = sqrtf(l2);
-                r_l1[rr] = l1; r_l2[rr] = nrm;
+                r_l1[rr] = l1; r_nrm[rr] = nrm;
                 r_inv[rr] = nrm > 1e-7f ? 1.f / fmaxf(nrm, 1e-8f) : 0.f;
-                r_cnt[rr] = cnt; r_k[rr] = lkmax; r_val[rr] = v1;
+                r_cnt[rr] = cnt; r_k[rr] = k1; r_val[rr] = v1;
             }
         }
         __syncthreads();
 
-        // ---- phase B: ordered bookkeeping by one thread ...
-        if (tid == NT - 1) {
+        // ---- phase B
+        // every thread: masks of the tile's general rows (valid for the solver / valid for the average)
+        unsigned gmask = 0, amask = 0;
+        for (int rr = 0; rr < rows; ++rr) {
+            const bool gen = r_cnt[rr] >= 2;
+            if (gen && r_l1[rr] > 1e-7f) gmask |= 1u << rr;          // src/cave.py:303
+            if (gen && r_inv[rr] != 0.f) amask |= 1u << rr;          // src/cave.py:224-225
+        }
+        if (tid == NT - 1) {                                         // ordered bookkeeping of the other rows
             for (int rr = 0; rr < rows; ++rr) {
-                const bool nv = r_l1[rr] > 1e-7f;       // src/cave.py:303
-                const bool av = r_inv[rr] != 0.f;       // src/cave.py:224-225
-                const int cnt = r_cnt[rr];
+                const bool nv = r_l1[rr] > 1e-7f, av = r_inv[rr] != 0.f;
                 c_nvalid += nv; c_navg += av;
-                if (cnt == 1) {
+                if (r_cnt[rr] == 1) {
                     const int k = r_k[rr];
                     const bool pos = r_val[rr] > 0.f;
                     if (nv) ctype[k] |= pos ? 1 : 2;
                     if (av) sing[k] += pos ? 1 : -1;
-                } else if (cnt >= 2 && nv) {
-                    gen_out[c_ngen++] = make_int2(t * R + rr, cnt);
-                    c_gennnz += cnt;
                 }
             }
         }
-        // ... while every thread accumulates its columns over the general rows of the tile
-        for (int k = tid; k < d; k += NT) {
-            float acc = 0.f;
-            for (int rr = 0; rr < rows; ++rr)
-                if (r_cnt[rr] >= 2 && r_inv[rr] != 0.f) acc = fmaf(tile[(size_t)rr * d + k], r_inv[rr], acc);
-            avg_gen[k] += acc;
+        if (amask) {                                                 // a / ||a|| over the general rows
+            for (int k = tid; k < d; k += NT) {
+                float acc = 0.f;
+                for (unsigned m = amask; m; m &= m - 1) {
+                    const int rr = __ffs(m) - 1;
+                    acc = fmaf(tile[(size_t)rr * d + k], r_inv[rr], acc);
+                }
+                avg_gen[k] += acc;
+            }
+        }
+        if (gmask) {                                                 // pack the general rows (CSR)
+            int ord = 0, off = t_gennnz;
+            for (unsigned m = gmask; m; m &= m - 1, ++ord) {
+                const int rr = __ffs(m) - 1;
+                const int cnt = r_cnt[rr];
+                if (ord % NW == warp) {
+                    uint64_t hp = 0, hn = 0;
+                    if (off + cnt <= p.cap_nnz) {
+                        const float* row = tile + (size_t)rr * d;
+                        int w = off;
+                        for (int k0 = 0; k0 < d; k0 += 32) {
+                            const int k = k0 + lane;
+                            const float v = k < d ? row[k] : 0.f;
+                            const unsigned nzm = __ballot_sync(0xffffffffu, v != 0.f);
+                            if (v != 0.f) {
+                                const int pos = w + __popc(nzm & ((1u << lane) - 1u));
+                                col_out[pos] = (uint16_t)k; val_out[pos] = v;
+                                const uint32_t bits = __float_as_uint(v);
+                                hp += mix64d(((uint64_t)k << 32) | bits);
+                                hn += mix64d(((uint64_t)k << 32) | (bits ^ 0x80000000u));
+                            }
+                            w += __popc(nzm);
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            hp += __shfl_xor_sync(0xffffffffu, hp, o);
+                            hn += __shfl_xor_sync(0xffffffffu, hn, o);
+                        }
+                    }
+                    if (lane == 0) {
+                        gen_out[t_ngen + ord] = make_int2(t * R + rr, cnt);
+                        hash_out[t_ngen + ord] = make_ulonglong2(hp, hn);
+                    }
+                }
+                if (off + cnt > p.cap_nnz) overflow = 1;
+                off += cnt;
+                t_l1max = fmaxf(t_l1max, r_l1[rr]);
+                t_l2max = fmaxf(t_l2max, r_nrm[rr] * r_nrm[rr]);
+            }
+            t_ngen += ord; t_gennnz = off;
         }
         __syncthreads();
         if (tid == 0 && t + S < ntiles) {
@@ -164,7 +271,7 @@ __global__ void __launch_bounds__(NT) scan_kernel(ScanParams p) {
         }
     }
 
-    if (tid == NT - 1) { s_cnt[0] = c_nvalid; s_cnt[1] = c_navg; s_cnt[2] = c_ngen; s_cnt[3] = c_gennnz; }
+    if (tid == NT - 1) { s_cnt[0] = c_nvalid; s_cnt[1] = c_navg; }
     __syncthreads();
     int nsc = 0;
     for (int k = tid; k < d; k += NT) nsc += ctype[k] != 0;
@@ -177,7 +284,9 @@ __global__ void __launch_bounds__(NT) scan_kernel(ScanParams p) {
     uint32_t* ct_out = (uint32_t*)(p.ctype + (size_t)b * p.dpad);
     for (int k = tid; k < (int)(p.dpad / 4); k += NT) ct_out[k] = ((const uint32_t*)ctype)[k];
     if (tid == 0) {
-        p.nvalid[b] = s_cnt[0]; p.navg[b] = s_cnt[1]; p.ngen[b] = s_cnt[2]; p.gennnz[b] = s_cnt[3]; p.nsingc[b] = s_cnt[4];
+        p.nvalid[b] = s_cnt[0]; p.navg[b] = s_cnt[1]; p.ngen[b] = t_ngen; p.gennnz[b] = t_gennnz; p.nsingc[b] = s_cnt[4];
+        p.csr_ok[b] = overflow ? 0 : 1;
+        p.maxl1[b] = t_l1max; p.maxl2[b] = t_l2max;
     }
 }
 
@@ -185,10 +294,10 @@ size_t scan_smem_bytes(int d, int R, int stages, size_t* stage_stride_out) {
     const size_t stride = align_up((size_t)R * d * 4 + 32, 128);
     const int64_t dpad = (int64_t)align_up((size_t)d, 16);
     size_t o = (size_t)stages * stride;
-    o += (size_t)d * 8;                 // avg_gen, sing
-    o += (size_t)R * 24;                // row arrays
-    o += 8 * 4 + 8;                     // counters (+ alignment)
+    o += (size_t)d * 8 + 8;             // avg_gen, sing (+ alignment)
     o += (size_t)stages * 8;            // mbarriers
+    o += (size_t)R * 24;                // row arrays
+    o += 8 * 4 + 16;                    // counters (+ alignment)
     o += (size_t)dpad;                  // ctype
     if (stage_stride_out) *stage_stride_out = stride;
     return align_up(o, 16);

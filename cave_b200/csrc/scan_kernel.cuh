@@ -15,6 +15,13 @@ struct ScanParams {
     int2* gen;
     unsigned char* ctype;
     float* avg;
+    // packed CSR of the general rows (per instance capacity cap_nnz) + row hashes for +-row matching
+    ulonglong2* ghash;
+    uint16_t* csr_col;
+    float* csr_val;
+    int cap_nnz;
+    int* csr_ok;            // 1 if every general row of the instance fitted into the packed CSR
+    float *maxl1, *maxl2;   // max_i ||a_i||_1 and max_i ||a_i||_2^2 over the general rows
 };
 
 cudaError_t launch_scan(const ScanParams& p, cudaStream_t stream);

@@ -36,6 +36,10 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(SolveParams p) {
         in.ctype = p.ctype + (size_t)b * p.dpad;
         in.avg = p.avg + (size_t)b * p.dpad;
         in.d = p.d; in.ngen = p.ngen[b]; in.gen_nnz = p.gennnz[b]; in.nvalid = p.nvalid[b]; in.nsingc = p.nsingc[b];
+        in.csr_ok = p.csr_ok[b]; in.maxl1 = p.maxl1[b]; in.maxl2 = p.maxl2[b];
+        in.ghash = p.ghash + (size_t)b * p.m_max;
+        in.pcol = p.csr_col + (size_t)b * p.cap_nnz;
+        in.pval = p.csr_val + (size_t)b * p.cap_nnz;
         Arena ar; ar.init(smem, p.smem_bytes, slot, p.slot_bytes);
         solve_instance<T, TIO>(cx, in, ar, pred + (size_t)b * p.d, ep, opt, grad + (size_t)b * p.d,
                                proj ? proj + (size_t)b * p.d : nullptr, p.loss64 + b, p.rnorm64 + b,

@@ -16,6 +16,12 @@ struct SolveParams {
     const int2* gen;
     const unsigned char* ctype;
     const float* avg;
+    const int* csr_ok;
+    const float *maxl1, *maxl2;
+    const ulonglong2* ghash;
+    const uint16_t* csr_col;
+    const float* csr_val;
+    int64_t cap_nnz;
     // scratch
     int* counter;
     double *loss64, *rnorm64;

@@ -28,11 +28,14 @@ namespace cave {
 #ifdef CAVE_HOST_SIM
 struct int2_ { int x, y; };
 typedef int2_ gen_t;
+struct u64x2_ { uint64_t x, y; };
+typedef u64x2_ hash_t;
 struct float4_ { float x, y, z, w; };
 typedef float4_ f4_t;
 #else
 typedef int2 gen_t;
 typedef float4 f4_t;
+typedef ulonglong2 hash_t;
 #endif
 
 enum { ST_CONVERGED = 0, ST_ITER_CAP = 1, ST_STALLED = 2, ST_NOSPACE = 3, ST_SKIPPED = 4, ST_PATH_LH = 0x100 };
@@ -138,6 +141,12 @@ struct Instance {
     const uint8_t* ctype;   // [d] singleton cone type per coordinate            (from the pack)
     const float* avg;       // [d] average unit normal (src/cave.py:222-228)     (from the pack)
     int d, ngen, gen_nnz, nvalid, nsingc;
+    // packed CSR of the general rows written by the scan kernel (valid iff csr_ok)
+    int csr_ok;
+    const hash_t* ghash;    // per general row: hash(row), hash(-row)
+    const uint16_t* pcol;
+    const float* pval;
+    float maxl1, maxl2;     // max ||a_i||_1, max ||a_i||_2^2 over the general rows
 };
 
 template <class T>
@@ -154,20 +163,23 @@ struct NewtonWork {
     T *c, *r, *rt;
     const uint8_t* ctype;
     int* rptr; uint16_t* rcol; float* rval;      // CSR of the general rows
-    uint8_t* rtype;                               // 0 bounded, 1 free (merged +-), 2 dropped
     int* grow;                                    // general row -> row index in A
+    uint8_t* rtype;                               // 0 bounded, 1 free (merged +-), 2 dropped
     int* vrow;                                    // variable -> CSR row
     uint8_t* vfree;                               // variable is sign-free
     int* cptr; uint16_t* crow; float* cval;      // CSC over variables
     T *nu, *g, *dir, *nut;
     int* flist;                                   // free-set variable ids
     int* fpos;                                    // variable -> position in flist or -1
-    f4_t* scr4;                                   // [d] dense scratch, 4 rows at a time
-    TH* H; TH* diagL; TH* dF;                      // Hessian / Cholesky factor precision
+    int* cur;                                     // [d] CSC fill cursors, later reused as wflag
+    uint8_t* wflag;                               // [d] psi'(r_k) currently folded into H
+    TH* H;                                        // [nv, nv] lower triangle of B W B^T, kept up to date
+    TH* L;                                        // [(nf+1), ldl] LDL^T work array with the rhs as last row
+    TH* xs;                                       // [nv] Newton step on the free set
 };
 
 template <class T, class TH>
-CAVE_DEV T nw_eval(Ctx& cx, const NewtonWork<T, TH>& W, const T* nu, T* rout) {
+CAVE_DEV void nw_eval2(Ctx& cx, const NewtonWork<T, TH>& W, const T* nu, T* rout, T& f, T& extra) {
     T acc = (T)0;
     for (int k = cx.tid; k < W.d; k += cx.nthr) {
         T rk = W.c[k];
@@ -176,7 +188,8 @@ CAVE_DEV T nw_eval(Ctx& cx, const NewtonWork<T, TH>& W, const T* nu, T* rout) {
         T q = psi(rk, (int)W.ctype[k]);
         acc += q * q;
     }
-    return (T)0.5 * cx.block_sum(acc);
+    cx.block_sum2(acc, extra);
+    f = (T)0.5 * acc;
 }
 
 template <class T, class TH>
@@ -194,50 +207,53 @@ CAVE_DEV void nw_grad(Ctx& cx, const NewtonWork<T, TH>& W, const T* r, T* g) {
     cx.sync();
 }
 
-// H[b][a] = sum_k W_k B[f_b][k] B[f_a][k] for b >= a (lower triangle), four rows `a` per pass.
+// Fold the columns whose activity psi'(r_k) changed since the last call into H = B W B^T
+// (lower triangle over ALL variables): H += +-b_k b_k^T with shared-memory atomics.  After the
+// first iterations only a handful of coordinates change sign, so this is almost free.
 template <class T, class TH>
-CAVE_DEV void nw_hessian(Ctx& cx, const NewtonWork<T, TH>& W, const T* r, int nf) {
-    for (int a0 = 0; a0 < nf; a0 += 4) {
-        int nb = nf - a0 < 4 ? nf - a0 : 4;
-        for (int rb = 0; rb < nb; ++rb) {
-            int row = W.vrow[W.flist[a0 + rb]];
-            for (int e = W.rptr[row] + cx.tid; e < W.rptr[row + 1]; e += cx.nthr) {
-                int k = W.rcol[e];
-                if (psi_active(r[k], (int)W.ctype[k])) ((float*)&W.scr4[k])[rb] = W.rval[e];
+CAVE_DEV void nw_hessian_update(Ctx& cx, const NewtonWork<T, TH>& W, const T* r) {
+    const int nv = W.nv;
+    for (int k = cx.tid; k < W.d; k += cx.nthr) {
+        const uint8_t now = psi_active(r[k], (int)W.ctype[k]) ? 1 : 0;
+        if (now == W.wflag[k]) continue;
+        W.wflag[k] = now;
+        const TH sg = now ? (TH)1 : (TH)-1;
+        const int s = W.cptr[k], e = W.cptr[k + 1];
+        for (int e1 = s; e1 < e; ++e1) {
+            const int a = W.crow[e1];
+            const TH va = sg * (TH)W.cval[e1];
+            for (int e2 = s; e2 <= e1; ++e2) {
+                const int b = W.crow[e2];
+                const int hi = a > b ? a : b, lo = a > b ? b : a;
+                cx.atomic_addf(&W.H[(size_t)hi * nv + lo], va * (TH)W.cval[e2]);
             }
         }
-        cx.sync();
-        for (int b = a0 + cx.warp; b < nf; b += cx.nwarp) {
-            int row = W.vrow[W.flist[b]];
-            TH s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            for (int e = W.rptr[row] + cx.lane; e < W.rptr[row + 1]; e += Ctx::WS) {
-                f4_t s = W.scr4[W.rcol[e]];
-                TH v = (TH)W.rval[e];
-                s0 += v * (TH)s.x; s1 += v * (TH)s.y; s2 += v * (TH)s.z; s3 += v * (TH)s.w;
-            }
-            s0 = cx.warp_sum(s0); s1 = cx.warp_sum(s1); s2 = cx.warp_sum(s2); s3 = cx.warp_sum(s3);
-            if (cx.lane == 0) {
-                TH* hb = W.H + (size_t)b * nf + a0;
-                if (a0 + 0 <= b) hb[0] = s0;
-                if (nb > 1 && a0 + 1 <= b) hb[1] = s1;
-                if (nb > 2 && a0 + 2 <= b) hb[2] = s2;
-                if (nb > 3 && a0 + 3 <= b) hb[3] = s3;
-            }
-        }
-        cx.sync();
-        for (int rb = 0; rb < nb; ++rb) {
-            int row = W.vrow[W.flist[a0 + rb]];
-            for (int e = W.rptr[row] + cx.tid; e < W.rptr[row + 1]; e += cx.nthr)
-                ((float*)&W.scr4[W.rcol[e]])[rb] = 0.f;
-        }
-        cx.sync();
+    }
+    cx.sync();
+}
+
+// Inclusive scan of x[0..n) in place by warp 0 (callers synchronise before and after).
+CAVE_DEV void warp0_inclusive_scan(Ctx& cx, int* x, int n) {
+    if (cx.warp != 0) return;
+    int carry = 0;
+    for (int i0 = 0; i0 < n; i0 += Ctx::WS) {
+        const int i = i0 + cx.lane;
+        int v = i < n ? x[i] : 0;
+#ifndef CAVE_HOST_SIM
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, v, o); if (cx.lane >= o) v += u; }
+#endif
+        v += carry;
+        if (i < n) x[i] = v;
+        carry = cx.shfl(v, Ctx::WS - 1);
     }
 }
 
-// Build CSR of the general rows from A, merge +- pairs, build the variable list and the CSC.
+// Bring the CSR of the general rows into the arena (from the scan kernel's pack, or by reading the
+// rows of A when the pack could not hold them), merge +- pairs, build the variable list and the CSC.
 // Returns false (arena overflow) if the instance does not fit the scratch caps.
 template <class T, class TH>
-CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH>& W, T* maxrow_l1) {
+CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH>& W, T* maxrow_l1, T* maxrow_l2sq) {
     const int d = in.d, mB = in.ngen;
     W.d = d; W.mB = mB; W.ctype = in.ctype;
     W.nu = ar.get<T>(mB + 1); W.g = ar.get<T>(mB + 1); W.dir = ar.get<T>(mB + 1); W.nut = ar.get<T>(mB + 1);
@@ -246,87 +262,108 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH>
     W.rtype = ar.get<uint8_t>(mB + 1);
     W.vrow = ar.get<int>(mB + 1);
     W.vfree = ar.get<uint8_t>(mB + 1);
-    W.flist = ar.get<int>(mB + 1);
-    W.fpos = ar.get<int>(mB + 1);
-    uint64_t* key = ar.get<uint64_t>(mB + 1);
+    W.flist = ar.get<int>(mB + 2);
+    W.fpos = ar.get<int>(mB + 2);
+    uint64_t* hpos = ar.get<uint64_t>(mB + 1);
+    uint64_t* hneg = ar.get<uint64_t>(mB + 1);
     int* cand = ar.get<int>(mB + 1);
-    W.diagL = ar.get<TH>(mB + 1);
-    W.dF = ar.get<TH>(mB + 1);
-    W.scr4 = ar.get<f4_t>(d);
+    W.xs = ar.get<TH>(mB + 2);
+    W.cur = ar.get<int>(d + 1);
+    W.wflag = (uint8_t*)W.cur;
     W.cptr = ar.get<int>(d + 2);
-    W.rcol = ar.get<uint16_t>(in.gen_nnz + 1);
-    W.rval = ar.get<float>(in.gen_nnz + 1);
+    W.rcol = ar.get<uint16_t>(in.gen_nnz + 8);
+    W.rval = ar.get<float>(in.gen_nnz + 4);
     if (ar.overflow) return false;
 
-    // row pointers (exclusive scan of the per-row counts the scan kernel stored)
-    for (int i = cx.tid; i < mB; i += cx.nthr) { gen_t g = in.gen[i]; W.grow[i] = g.x; W.rptr[i + 1] = g.y; }
-    for (int k = cx.tid; k < d; k += cx.nthr) { f4_t z; z.x = z.y = z.z = z.w = 0.f; W.scr4[k] = z; }
-    cx.sync();
-    if (cx.tid == 0) {
-        int acc = 0;
-        for (int i = 0; i < mB; ++i) { int n = W.rptr[i + 1]; W.rptr[i] = acc; acc += n; }
-        W.rptr[mB] = acc;
-    }
-    cx.sync();
-    // fill: one warp per row, ballot compaction keeps the columns sorted
-    T l1max = (T)0;
-    for (int i = cx.warp; i < mB; i += cx.nwarp) {
-        const float* row = in.A + (size_t)W.grow[i] * d;
-        int off = W.rptr[i];
-        uint64_t kacc = 0;
-        float l1 = 0.f;
-        for (int k0 = 0; k0 < d; k0 += Ctx::WS * 4) {
-            float v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                int k = k0 + u * Ctx::WS + cx.lane;
-                v[u] = k < d ? ld_stream(row + k) : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                int k = k0 + u * Ctx::WS + cx.lane;
-                bool nz = v[u] != 0.f;
-                unsigned m = cx.ballot(nz);
-                if (nz) {
-                    int p = off + cx.lanes_below(m);
-                    W.rcol[p] = (uint16_t)k; W.rval[p] = v[u];
-                    union { float f; uint32_t u; } cv; cv.f = v[u];
-                    kacc += mix64(((uint64_t)k << 32) | (cv.u & 0x7fffffffu));
-                    l1 += v[u] < 0.f ? -v[u] : v[u];
-                }
-#ifdef CAVE_HOST_SIM
-                off += nz ? 1 : 0;
-#else
-                off += __popc(m);
-#endif
-            }
-        }
-        // wrapping 64-bit sum over lanes
-        uint32_t lo = (uint32_t)kacc, hi = (uint32_t)(kacc >> 32);
-#ifndef CAVE_HOST_SIM
-        for (int o = 16; o > 0; o >>= 1) {
-            uint64_t other = ((uint64_t)__shfl_xor_sync(0xffffffffu, hi, o) << 32) | __shfl_xor_sync(0xffffffffu, lo, o);
-            kacc += other; lo = (uint32_t)kacc; hi = (uint32_t)(kacc >> 32);
-        }
-#endif
-        l1 = cx.warp_sum(l1);
-        if (cx.lane == 0) key[i] = kacc;
-        if ((T)l1 > l1max) l1max = (T)l1;
-    }
-    *maxrow_l1 = cx.block_max(l1max);   // (barriers inside make the CSR visible)
-
-    // merge b_j = -b_i : cand[i] = smallest j != i with row_j == -row_i; merged iff mutual
+    if (cx.tid == 0) W.rptr[0] = 0;
     for (int i = cx.tid; i < mB; i += cx.nthr) {
-        int c0 = -1;
-        int ni = W.rptr[i + 1] - W.rptr[i];
-        for (int j = 0; j < mB && c0 < 0; ++j) {
-            if (j == i || key[j] != key[i] || W.rptr[j + 1] - W.rptr[j] != ni) continue;
-            bool ok = true;
-            for (int e = 0; e < ni && ok; ++e)
-                ok = W.rcol[W.rptr[i] + e] == W.rcol[W.rptr[j] + e] && W.rval[W.rptr[i] + e] == -W.rval[W.rptr[j] + e];
-            if (ok) c0 = j;
+        gen_t g = in.gen[i]; W.grow[i] = g.x; W.rptr[i + 1] = g.y;
+        if (in.csr_ok) { hash_t h = in.ghash[i]; hpos[i] = h.x; hneg[i] = h.y; }
+    }
+    cx.sync();
+    warp0_inclusive_scan(cx, W.rptr + 1, mB);
+    if (in.csr_ok) {
+        // the scan kernel already compacted the rows: 16-byte copies global -> arena
+#ifdef CAVE_HOST_SIM
+        for (int e = 0; e < in.gen_nnz; ++e) { W.rcol[e] = in.pcol[e]; W.rval[e] = in.pval[e]; }
+#else
+        const int n16c = (in.gen_nnz * 2 + 15) >> 4, n16v = (in.gen_nnz * 4 + 15) >> 4;
+        const uint4* sc = (const uint4*)in.pcol; uint4* dc = (uint4*)W.rcol;
+        const uint4* sv = (const uint4*)in.pval; uint4* dv = (uint4*)W.rval;
+        for (int t = cx.tid; t < n16c; t += cx.nthr) dc[t] = __ldg(sc + t);
+        for (int t = cx.tid; t < n16v; t += cx.nthr) dv[t] = __ldg(sv + t);
+#endif
+        *maxrow_l1 = (T)in.maxl1; *maxrow_l2sq = (T)in.maxl2;
+        cx.sync();
+    } else {
+        cx.sync();
+        // fallback: one warp per row of A, ballot compaction keeps the columns sorted
+        T l1max = (T)0, l2max = (T)0;
+        for (int i = cx.warp; i < mB; i += cx.nwarp) {
+            const float* row = in.A + (size_t)W.grow[i] * d;
+            int off = W.rptr[i];
+            uint64_t hp = 0, hn = 0;
+            float l1 = 0.f, l2 = 0.f;
+            for (int k0 = 0; k0 < d; k0 += Ctx::WS * 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    int k = k0 + u * Ctx::WS + cx.lane;
+                    v[u] = k < d ? ld_stream(row + k) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    int k = k0 + u * Ctx::WS + cx.lane;
+                    bool nz = v[u] != 0.f;
+                    unsigned m = cx.ballot(nz);
+                    if (nz) {
+                        int p = off + cx.lanes_below(m);
+                        W.rcol[p] = (uint16_t)k; W.rval[p] = v[u];
+                        union { float f; uint32_t u; } cv; cv.f = v[u];
+                        hp += mix64(((uint64_t)k << 32) | cv.u);
+                        hn += mix64(((uint64_t)k << 32) | (cv.u ^ 0x80000000u));
+                        l1 += v[u] < 0.f ? -v[u] : v[u];
+                        l2 += v[u] * v[u];
+                    }
+                    off += cx.popc(m);
+                }
+            }
+            hp = cx.warp_sum_u64(hp); hn = cx.warp_sum_u64(hn);
+            l1 = cx.warp_sum(l1); l2 = cx.warp_sum(l2);
+            if (cx.lane == 0) { hpos[i] = hp; hneg[i] = hn; }
+            if ((T)l1 > l1max) l1max = (T)l1;
+            if ((T)l2 > l2max) l2max = (T)l2;
         }
-        cand[i] = c0;
+        cx.block_max2(l1max, l2max);    // (barriers inside make the CSR visible)
+        *maxrow_l1 = l1max; *maxrow_l2sq = l2max;
+    }
+
+    // merge b_j = -b_i : cand[i] = smallest j != i with row_j == -row_i (hash match, then an exact
+    // comparison); merged iff the choice is mutual.  One warp per row.
+    for (int i = cx.warp; i < mB; i += cx.nwarp) {
+        const int ni = W.rptr[i + 1] - W.rptr[i], pi = W.rptr[i];
+        const uint64_t want = hneg[i];
+        int c0 = -1;
+        for (int j0 = 0; j0 < mB && c0 < 0; j0 += Ctx::WS) {
+            const int j = j0 + cx.lane;
+            bool hit = j < mB && j != i && hpos[j] == want && W.rptr[j + 1] - W.rptr[j] == ni;
+            unsigned m = cx.ballot(hit);
+            while (m && c0 < 0) {
+#ifdef CAVE_HOST_SIM
+                const int jj = j0;
+#else
+                const int jj = j0 + __ffs(m) - 1;
+#endif
+                const int pj = W.rptr[jj];
+                bool ok = true;
+                for (int e = cx.lane; e < ni; e += Ctx::WS)
+                    ok = ok && W.rcol[pi + e] == W.rcol[pj + e] && W.rval[pi + e] == -W.rval[pj + e];
+                const unsigned bad = cx.ballot(!ok);
+                if (!bad) c0 = jj;
+                m &= m - 1;
+            }
+        }
+        if (cx.lane == 0) cand[i] = c0;
     }
     cx.sync();
     for (int i = cx.tid; i < mB; i += cx.nthr) {
@@ -334,38 +371,50 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH>
         W.rtype[i] = (j >= 0 && cand[j] == i) ? (i < j ? 1 : 2) : 0;
     }
     cx.sync();
-    // variables = rows that were not dropped; count CSC entries
-    if (cx.tid == 0) {
-        int nv = 0, nz = 0;
-        for (int i = 0; i < mB; ++i)
-            if (W.rtype[i] != 2) { W.vrow[nv] = i; W.vfree[nv] = W.rtype[i] == 1; ++nv; nz += W.rptr[i + 1] - W.rptr[i]; }
-        W.flist[0] = nv; W.flist[1] = nz;   // broadcast through shared/global memory
+    // variables = rows that were not dropped (ordered compaction by warp 0); count CSC entries
+    if (cx.warp == 0) {
+        int nvb = 0, nz = 0;
+        for (int i0 = 0; i0 < mB; i0 += Ctx::WS) {
+            const int i = i0 + cx.lane;
+            const bool keep = i < mB && W.rtype[i] != 2;
+            const unsigned m = cx.ballot(keep);
+            if (keep) {
+                const int v = nvb + cx.lanes_below(m);
+                W.vrow[v] = i; W.vfree[v] = W.rtype[i] == 1;
+                nz += W.rptr[i + 1] - W.rptr[i];
+            }
+            nvb += cx.popc(m);
+        }
+        nz = cx.warp_sum(nz);
+        if (cx.lane == 0) { W.flist[0] = nvb; W.flist[1] = nz; }   // broadcast through memory
     }
     cx.sync();
     W.nv = W.flist[0];
-    int nnzc = W.flist[1];
+    const int nnzc = W.flist[1];
     cx.sync();
-    W.H = ar.get<TH>((size_t)W.nv * W.nv + 1);
+    const int nv = W.nv;
+    W.H = ar.get<TH>((size_t)nv * nv + 1);
+    W.L = ar.get<TH>((size_t)(nv + 1) * ((nv + 1) | 1) + 1);
     W.crow = ar.get<uint16_t>(nnzc + 1);
     W.cval = ar.get<float>(nnzc + 1);
     if (ar.overflow) return false;
     // CSC: count, scan, fill with a cursor, then order every column by variable id
-    int* cur = (int*)W.scr4;     // d ints, scratch is free here
     for (int k = cx.tid; k <= d; k += cx.nthr) W.cptr[k] = 0;
+    for (size_t t = cx.tid; t < (size_t)nv * nv; t += cx.nthr) W.H[t] = (TH)0;
     cx.sync();
-    for (int v = cx.warp; v < W.nv; v += cx.nwarp) {
+    for (int v = cx.warp; v < nv; v += cx.nwarp) {
         int row = W.vrow[v];
         for (int e = W.rptr[row] + cx.lane; e < W.rptr[row + 1]; e += Ctx::WS) cx.atomic_add(&W.cptr[W.rcol[e] + 1], 1);
     }
     cx.sync();
-    if (cx.tid == 0) { for (int k = 0; k < d; ++k) W.cptr[k + 1] += W.cptr[k]; }
+    warp0_inclusive_scan(cx, W.cptr + 1, d);
     cx.sync();
-    for (int k = cx.tid; k < d; k += cx.nthr) cur[k] = W.cptr[k];
+    for (int k = cx.tid; k < d; k += cx.nthr) W.cur[k] = W.cptr[k];
     cx.sync();
-    for (int v = cx.warp; v < W.nv; v += cx.nwarp) {
+    for (int v = cx.warp; v < nv; v += cx.nwarp) {
         int row = W.vrow[v];
         for (int e = W.rptr[row] + cx.lane; e < W.rptr[row + 1]; e += Ctx::WS) {
-            int p = cx.atomic_add(&cur[W.rcol[e]], 1);
+            int p = cx.atomic_add(&W.cur[W.rcol[e]], 1);
             W.crow[p] = (uint16_t)v; W.cval[p] = W.rval[e];
         }
     }
@@ -380,7 +429,7 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH>
             }
     }
     cx.sync();
-    for (int k = cx.tid; k < d; k += cx.nthr) { f4_t z; z.x = z.y = z.z = z.w = 0.f; W.scr4[k] = z; }
+    for (int k = cx.tid; k < d; k += cx.nthr) W.wflag[k] = 0;     // (aliases cur: H starts empty)
     cx.sync();
     return true;
 }
@@ -390,19 +439,22 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, T* c, T* r, T
                            const SolveOpts& opt, Result<T>& out) {
     NewtonWork<T, TH> W;
     W.c = c; W.r = r; W.rt = rt;
-    T l1max;
-    if (!nw_setup(cx, in, ar, W, &l1max)) { out.status = ST_NOSPACE; out.iters = 0; out.r = r; return; }
+    T l1max, l2max;
+    if (!nw_setup(cx, in, ar, W, &l1max, &l2max)) { out.status = ST_NOSPACE; out.iters = 0; out.r = r; return; }
     const int nv = W.nv;
     const T scale = (l1max > (T)1 ? l1max : (T)1) * (cnorm > (T)1e-30 ? cnorm : (T)1e-30);
-    const T tol = (T)(opt.tol > 0 ? opt.tol : (sizeof(T) == 8 ? 1e-12 : 2e-6)) * scale;
+    const T tol = (T)(opt.tol > 0 ? opt.tol : 1e-12) * scale;
     const int max_iter = opt.max_iter > 0 ? opt.max_iter : 200;
     const int max_ls = opt.max_ls > 0 ? opt.max_ls : 40;
-    const TH delta = sizeof(TH) == 8 ? (TH)1e-11 : (TH)2e-6;   // Tikhonov term, relative to max diag
+    // Tikhonov term: relative to the largest possible diagonal entry of B W B^T (max_i ||b_i||^2)
+    const TH reg = (sizeof(TH) == 8 ? (TH)1e-11 : (TH)2e-6) * (TH)(l2max > (T)0 ? l2max : (T)1);
+    const TH piv_floor = eps_mach<TH>() * (TH)(l2max > (T)0 ? l2max : (T)1);
 
     for (int v = cx.tid; v < nv; v += cx.nthr) W.nu[v] = (T)0;
     cx.sync();
     T *nu = W.nu, *nut = W.nut, *rc = W.r, *rn = W.rt;
-    T f = nw_eval(cx, W, nu, rc);
+    T f, dummy = (T)0;
+    nw_eval2(cx, W, nu, rc, f, dummy);
     int status = ST_ITER_CAP, it = 0;
     for (; it < max_iter; ++it) {
         nw_grad(cx, W, rc, W.g);
@@ -415,32 +467,82 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, T* c, T* r, T
         }
         res = cx.block_max(res);
         if (!(res > tol)) { status = ST_CONVERGED; break; }
-        T epsb = res < (T)1e-3 ? res : (T)1e-3;
-        if (cx.tid == 0) {      // ordered free list (every variable that is not epsilon-binding)
-            int nf = 0;
-            for (int v = 0; v < nv; ++v) {
-                bool bind = !W.vfree[v] && nu[v] <= epsb && W.g[v] > (T)0;
-                W.fpos[v] = bind ? -1 : nf;
-                if (!bind) W.flist[nf++] = v;
+        const T epsb = res < (T)1e-3 ? res : (T)1e-3;
+        // ordered free list (every variable that is not epsilon-binding), built by warp 0
+        if (cx.warp == 0) {
+            int nfb = 0;
+            for (int v0 = 0; v0 < nv; v0 += Ctx::WS) {
+                const int v = v0 + cx.lane;
+                const bool isf = v < nv && !(!W.vfree[v] && nu[v] <= epsb && W.g[v] > (T)0);
+                const unsigned m = cx.ballot(isf);
+                if (v < nv) {
+                    const int pos = nfb + cx.lanes_below(m);
+                    W.fpos[v] = isf ? pos : -1;
+                    if (isf) W.flist[pos] = v;
+                }
+                nfb += cx.popc(m);
             }
-            W.fpos[nv] = nf;
+            if (cx.lane == 0) W.fpos[nv] = nfb;
+        }
+        nw_hessian_update(cx, W, rc);          // (ends with a barrier: flist / fpos visible too)
+        const int nf = W.fpos[nv];
+        const int ldl = (nf + 1) | 1;
+        // L <- [H_FF + reg I ; g_F^T]
+        for (int a = cx.warp; a <= nf; a += cx.nwarp) {
+            TH* la = W.L + (size_t)a * ldl;
+            if (a == nf) {
+                for (int b = cx.lane; b < nf; b += Ctx::WS) la[b] = (TH)W.g[W.flist[b]];
+            } else {
+                const TH* ha = W.H + (size_t)W.flist[a] * nv;       // flist ascending => flist[a] >= flist[b]
+                for (int b = cx.lane; b <= a; b += Ctx::WS) la[b] = ha[W.flist[b]] + (a == b ? reg : (TH)0);
+            }
+        }
+        // in-place LDL^T, unscaled columns; the rhs row turns into z = L^-1 g   (one barrier per column;
+        // four rows per warp with all loads issued before the stores)
+        for (int j = 0; j < nf; ++j) {
+            cx.sync();
+            TH dj = W.L[(size_t)j * ldl + j];
+            if (!(dj > piv_floor)) dj = piv_floor;
+            const TH inv = (TH)1 / dj;
+            const TH* colj = W.L + j;
+            for (int i0 = j + 1 + cx.warp * 4; i0 <= nf; i0 += cx.nwarp * 4) {
+                TH lij[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) lij[u] = (i0 + u <= nf) ? colj[(size_t)(i0 + u) * ldl] * inv : (TH)0;
+                const int ilast = i0 + 3 < nf ? i0 + 3 : nf;
+                const int kmax = ilast < nf ? ilast : nf - 1;
+                for (int k = j + 1 + cx.lane; k <= kmax; k += Ctx::WS) {
+                    const TH lkj = colj[(size_t)k * ldl];
+                    TH x[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u;
+                        x[u] = (i <= nf && (k <= i || i == nf)) ? W.L[(size_t)i * ldl + k] : (TH)0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u;
+                        if (i <= nf && (k <= i || i == nf)) W.L[(size_t)i * ldl + k] = x[u] - lij[u] * lkj;
+                    }
+                }
+            }
         }
         cx.sync();
-        const int nf = W.fpos[nv];
-        if (nf > 0) {
-            nw_hessian(cx, W, rc, nf);
-            TH dmax = (TH)0;
-            for (int a = cx.tid; a < nf; a += cx.nthr) { TH h = W.H[(size_t)a * nf + a]; dmax = h > dmax ? h : dmax; }
-            dmax = cx.block_max(dmax);
-            if (!(dmax > (TH)0)) dmax = (TH)1;
-            for (int a = cx.tid; a < nf; a += cx.nthr) W.H[(size_t)a * nf + a] += delta * dmax;
-            chol_factor(cx, W.H, nf, nf, W.diagL, eps_mach<TH>() * dmax);
+        // back substitution D L^T x = z by warp 0 (column oriented, no reductions)
+        if (cx.warp == 0) {
+            TH* z = W.L + (size_t)nf * ldl;
+            for (int j = nf - 1; j >= 0; --j) {
+                TH dj = W.L[(size_t)j * ldl + j];
+                if (!(dj > piv_floor)) dj = piv_floor;
+                const TH xj = z[j] / dj;
+                cx.syncwarp();
+                if (cx.lane == 0) W.xs[j] = xj;
+                for (int i = cx.lane; i < j; i += Ctx::WS) z[i] -= W.L[(size_t)j * ldl + i] * xj;
+                cx.syncwarp();
+            }
         }
-        // direction: Newton on the free set (solved in place in dir[0..nf)), gradient on the binding set
-        TH* dF = W.dF;
-        for (int a = cx.tid; a < nf; a += cx.nthr) dF[a] = (TH)W.g[W.flist[a]];
-        if (nf > 0) chol_solve(cx, W.H, nf, nf, W.diagL, dF); else cx.sync();
-        for (int v = cx.tid; v < nv; v += cx.nthr) W.dir[v] = W.fpos[v] >= 0 ? (T)dF[W.fpos[v]] : W.g[v];
+        cx.sync();
+        for (int v = cx.tid; v < nv; v += cx.nthr) W.dir[v] = W.fpos[v] >= 0 ? (T)W.xs[W.fpos[v]] : W.g[v];
         cx.sync();
         // Armijo along the projection arc
         T alpha = (T)1, ft = f;
@@ -453,8 +555,8 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, T* c, T* r, T
                 nut[v] = t;
                 dec += W.g[v] * (nu[v] - t);
             }
-            dec = cx.block_sum(dec);
-            ft = nw_eval(cx, W, nut, rn);
+            cx.sync();
+            nw_eval2(cx, W, nut, rn, ft, dec);
             if (ft <= f - (T)1e-4 * dec + (T)4 * eps_mach<T>() * f) { ok = true; break; }
             alpha *= (T)0.5;
         }

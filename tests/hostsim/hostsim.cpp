@@ -11,7 +11,9 @@ using namespace cave;
 // plain restatement of what the scan kernel (scan_kernel.cu) writes into the pack
 struct HostPack {
     std::vector<gen_t> gen; std::vector<uint8_t> ctype; std::vector<float> avg;
+    std::vector<hash_t> ghash; std::vector<uint16_t> col; std::vector<float> val;
     int nvalid = 0, navg = 0, gen_nnz = 0, nsingc = 0;
+    float maxl1 = 0.f, maxl2 = 0.f;
 };
 static void host_pack(const float* A, int m, int d, HostPack& pk) {
     pk.ctype.assign(d, 0); pk.avg.assign(d, 0.f);
@@ -28,7 +30,17 @@ static void host_pack(const float* A, int m, int d, HostPack& pk) {
             if (nv) pk.ctype[lk] |= lv > 0.f ? 1 : 2;
             if (av) sing[lk] += lv > 0.f ? 1 : -1;
         } else if (cnt >= 2) {
-            if (nv) { gen_t g; g.x = i; g.y = cnt; pk.gen.push_back(g); pk.gen_nnz += cnt; }
+            if (nv) {
+                gen_t g; g.x = i; g.y = cnt; pk.gen.push_back(g); pk.gen_nnz += cnt;
+                hash_t h; h.x = 0; h.y = 0;
+                for (int k = 0; k < d; ++k) if (row[k] != 0.f) {
+                    union { float f; uint32_t u; } cv; cv.f = row[k];
+                    h.x += mix64(((uint64_t)k << 32) | cv.u); h.y += mix64(((uint64_t)k << 32) | (cv.u ^ 0x80000000u));
+                    pk.col.push_back((uint16_t)k); pk.val.push_back(row[k]);
+                }
+                pk.ghash.push_back(h);
+                pk.maxl1 = fmaxf(pk.maxl1, l1); pk.maxl2 = fmaxf(pk.maxl2, nrm * nrm);
+            }
             if (av) for (int k = 0; k < d; ++k) gen_acc[k] += row[k] * inv;
         }
     }
@@ -46,7 +58,9 @@ static void run(const float* A, int B, int m, int d, const double* pred, double 
         HostPack pk; host_pack(A + (size_t)b * m * d, m, d, pk);
         Instance in; in.A = A + (size_t)b * m * d; in.gen = pk.gen.data(); in.ctype = pk.ctype.data(); in.avg = pk.avg.data();
         in.d = d; in.ngen = (int)pk.gen.size(); in.gen_nnz = pk.gen_nnz; in.nvalid = pk.nvalid; in.nsingc = pk.nsingc;
-        if (force_path == 1) in.nsingc = 0 == in.nsingc ? 1 : in.nsingc;      // force Newton
+        in.csr_ok = (force_path & 2) ? 0 : 1;                                  // bit 1: rebuild the CSR from A
+        in.ghash = pk.ghash.data(); in.pcol = pk.col.data(); in.pval = pk.val.data(); in.maxl1 = pk.maxl1; in.maxl2 = pk.maxl2;
+        if (force_path & 1) in.nsingc = 0 == in.nsingc ? 1 : in.nsingc;       // bit 0: force the Newton path
         Arena ar; ar.init(nullptr, 0, buf, cap);
         Ctx cx; EpiParams ep; ep.mode = mode; ep.inner_ratio = inner_ratio; ep.sign = sign; ep.gscale = gscale;
         SolveOpts opt; opt.max_iter = 0; opt.max_ls = 0; opt.tol = 0;

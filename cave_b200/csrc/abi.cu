@@ -49,7 +49,7 @@ int sm_count() {
 }
 
 int64_t solver_ctas(int64_t B) {
-    int64_t n = (int64_t)sm_count() * env_int("CAVE_SOLVE_CTAS_PER_SM", 1);
+    int64_t n = (int64_t)sm_count() * env_int("CAVE_SOLVE_CTAS_PER_SM", 2);
     return B < n ? B : n;
 }
 
@@ -169,10 +169,11 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     sp.counter = (int*)(sb + SL.counter); sp.loss64 = (double*)(sb + SL.loss64); sp.rnorm64 = (double*)(sb + SL.rnorm64);
     sp.status = (int*)(sb + SL.status); sp.iters = (int*)(sb + SL.iters);
     sp.slots = sb + SL.slots; sp.slot_bytes = SL.slot_bytes;
-    sp.smem_bytes = env_int("CAVE_SOLVE_SMEM", 220 * 1024);
+    sp.smem_bytes = env_int("CAVE_SOLVE_SMEM", 110 * 1024);   // two CTAs per SM
     sp.mode = mode; sp.inner_ratio = inner_ratio; sp.sign = sign;
     sp.gscale = reduction == CAVE_REDUCE_MEAN ? 1.0 / (double)B : 1.0;
     sp.max_iter = opts ? opts->max_iter : 0; sp.max_ls = opts ? opts->max_linesearch : 0; sp.tol = opts ? opts->tol : 0.0;
+    sp.profile = env_int("CAVE_PROFILE", 0);
     int threads = env_int("CAVE_SOLVE_THREADS", 256);
     if (threads != 128 && threads != 256 && threads != 512) threads = 256;
     ce = cave::launch_solve(sp, compute_dtype == CAVE_F32, io_dtype == CAVE_F32, (int)n_ctas, threads, st);
@@ -184,6 +185,16 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     fp.loss = loss; fp.loss_i = loss_i; fp.rnorm = rnorm; fp.status_out = status; fp.iters_out = iters;
     ce = cave::launch_finalize(fp, io_dtype == CAVE_F32, st);
     if (ce != cudaSuccess) return fail(CAVE_ECUDA, "finalize kernel launch failed: %s", cudaGetErrorString(ce));
+    return CAVE_OK;
+}
+
+/* debug aid (not part of the stable ABI): per-phase cycle counters of the solve kernel, filled
+ * when the environment variable CAVE_PROFILE=1 is set.  Synchronises the device. */
+int cave_debug_phase_cycles(unsigned long long* out32, int reset) {
+    if (!out32) return fail(CAVE_EINVAL, "out32 is null");
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cave::read_phase_cycles(out32, reset);
+    if (e != cudaSuccess) return fail(CAVE_ECUDA, "phase counter read failed: %s", cudaGetErrorString(e));
     return CAVE_OK;
 }
 

@@ -18,6 +18,8 @@ struct Ctx {
     int tid = 0, nthr = 1, lane = 0, warp = 0, nwarp = 1;
     void sync() {}
     void syncwarp() {}
+    void bar_named(int, int) {}
+    void phase(int) {}
     template <class T> T warp_sum(T v) { return v; }
     template <class T> T warp_max(T v) { return v; }
     template <class T> T block_sum(T v) { return v; }
@@ -37,6 +39,20 @@ struct Ctx {
     template <class T> T shfl(T v, int) { return v; }
 };
 CAVE_DEV float ld_stream(const float* p) { return *p; }
+
+// "Hot pointer": on the device with HOT = true a 32-bit shared-memory address whose element accesses are
+// explicit ld.shared / st.shared / atom.shared (the compiler does not reliably infer the address space
+// through the arena); with HOT = false, and always in the host simulation, a plain generic pointer.
+template <class U, bool HOT>
+struct HPtr {
+    U* p;
+    HPtr() : p(nullptr) {}
+    explicit HPtr(U* q) : p(q) {}
+    U& operator[](size_t i) const { return p[i]; }
+    HPtr operator+(size_t o) const { return HPtr(p + o); }
+    U* raw() const { return p; }
+    void atomic_add(size_t i, U v) const { p[i] += v; }
+};
 }  // namespace cave
 #else
 #define CAVE_DEV __device__ __forceinline__
@@ -46,11 +62,17 @@ struct Ctx {
     static constexpr int WS = 32;
     int tid, nthr, lane, warp, nwarp;
     double* red;   // shared scratch: >= 2 * 32 doubles
+    unsigned long long* prof = nullptr;   // optional [32] global cycle counters per phase (debug)
+    long long t_last = 0; int ph_cur = 0;
+    __device__ __forceinline__ void phase(int n) {
+        if (prof && tid == 0) { long long t = clock64(); atomicAdd(prof + ph_cur, (unsigned long long)(t - t_last)); t_last = t; ph_cur = n; }
+    }
     __device__ Ctx(double* red_) : red(red_) {
         tid = threadIdx.x; nthr = blockDim.x; lane = tid & 31; warp = tid >> 5; nwarp = nthr >> 5;
     }
     __device__ __forceinline__ void sync() { __syncthreads(); }
     __device__ __forceinline__ void syncwarp() { __syncwarp(); }
+    __device__ __forceinline__ void bar_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
     template <class T> __device__ __forceinline__ T shfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
     template <class T> __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
@@ -146,6 +168,58 @@ struct Ctx {
     __device__ __forceinline__ int lanes_below(unsigned mask) { return __popc(mask & ((1u << lane) - 1u)); }
     __device__ __forceinline__ int atomic_add(int* p, int v) { return atomicAdd(p, v); }
 };
+
+// ---- explicit shared-memory element access (see HPtr below)
+template <class U> struct SmemOps;
+template <> struct SmemOps<float> {
+    static __device__ __forceinline__ float ld(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+    static __device__ __forceinline__ void st(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+    static __device__ __forceinline__ void add(uint32_t a, float v) { asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+};
+template <> struct SmemOps<double> {
+    static __device__ __forceinline__ double ld(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+    static __device__ __forceinline__ void st(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+    static __device__ __forceinline__ void add(uint32_t a, double v) { asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+};
+template <> struct SmemOps<int> {
+    static __device__ __forceinline__ int ld(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+    static __device__ __forceinline__ void st(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+    static __device__ __forceinline__ void add(uint32_t a, int v) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+};
+template <> struct SmemOps<uint8_t> {
+    static __device__ __forceinline__ uint8_t ld(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return (uint8_t)v; }
+    static __device__ __forceinline__ void st(uint32_t a, uint8_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"((uint32_t)v) : "memory"); }
+    static __device__ __forceinline__ void add(uint32_t, uint8_t) {}
+};
+template <class U> struct SRef {
+    uint32_t a;
+    __device__ __forceinline__ operator U() const { return SmemOps<U>::ld(a); }
+    __device__ __forceinline__ const SRef& operator=(U v) const { SmemOps<U>::st(a, v); return *this; }
+    __device__ __forceinline__ const SRef& operator=(const SRef& o) const { SmemOps<U>::st(a, SmemOps<U>::ld(o.a)); return *this; }
+    __device__ __forceinline__ const SRef& operator-=(U v) const { SmemOps<U>::st(a, SmemOps<U>::ld(a) - v); return *this; }
+    __device__ __forceinline__ const SRef& operator+=(U v) const { SmemOps<U>::st(a, SmemOps<U>::ld(a) + v); return *this; }
+    __device__ __forceinline__ const SRef& operator*=(U v) const { SmemOps<U>::st(a, SmemOps<U>::ld(a) * v); return *this; }
+};
+template <class U, bool HOT> struct HPtr;
+template <class U> struct HPtr<U, true> {
+    uint32_t a;
+    __device__ __forceinline__ HPtr() : a(0) {}
+    __device__ __forceinline__ explicit HPtr(U* q) : a((uint32_t)__cvta_generic_to_shared(q)) {}
+    __device__ __forceinline__ SRef<U> operator[](size_t i) const { SRef<U> r; r.a = a + (uint32_t)i * (uint32_t)sizeof(U); return r; }
+    __device__ __forceinline__ HPtr operator+(size_t o) const { HPtr h; h.a = a + (uint32_t)o * (uint32_t)sizeof(U); return h; }
+    __device__ __forceinline__ U* raw() const { return (U*)__cvta_shared_to_generic((size_t)a); }
+    __device__ __forceinline__ void atomic_add(size_t i, U v) const { SmemOps<U>::add(a + (uint32_t)i * (uint32_t)sizeof(U), v); }
+};
+template <class U> struct HPtr<U, false> {
+    U* p;
+    __device__ __forceinline__ HPtr() : p(nullptr) {}
+    __device__ __forceinline__ explicit HPtr(U* q) : p(q) {}
+    __device__ __forceinline__ U& operator[](size_t i) const { return p[i]; }
+    __device__ __forceinline__ HPtr operator+(size_t o) const { return HPtr(p + o); }
+    __device__ __forceinline__ U* raw() const { return p; }
+    __device__ __forceinline__ void atomic_add(size_t i, U v) const { atomicAdd(p + i, v); }
+};
+
 // streaming global load that does not pollute L1 (rows of A are touched once per phase)
 CAVE_DEV float ld_stream(const float* p) {
     float v;

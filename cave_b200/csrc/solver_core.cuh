@@ -47,20 +47,35 @@ struct SolveOpts {
     double tol;        // relative KKT tolerance
 };
 
-// Two-level bump allocator: shared memory first, the CTA's global scratch slot after that.
+// Bump allocator over the CTA's shared memory and its global scratch slot.
+//   get_sm : "hot" arrays (vectors, Hessian, factor).  Shared memory only, taken from the front; the
+//            returned pointer is shared-base + offset with no generic select, so the compiler keeps the
+//            shared address space and emits LDS/STS/ATOMS for them.
+//   get    : "cold" arrays (sparse rows, setup scratch).  Taken from the back of shared memory while it
+//            lasts, then from the global slot; accessed through generic pointers.
 struct Arena {
-    char* sm; size_t sm_cap, sm_off;
+    char* sm; size_t sm_front, sm_back;
     char* gl; size_t gl_cap, gl_off;
-    bool overflow;
+    bool overflow, hot_overflow;
     CAVE_DEV void init(char* s, size_t sc, char* g, size_t gc) {
-        sm = s; sm_cap = sc; sm_off = 0; gl = g; gl_cap = gc; gl_off = 0; overflow = false;
+        sm = s; sm_front = 0; sm_back = sc & ~(size_t)15; gl = g; gl_cap = gc; gl_off = 0; overflow = false; hot_overflow = false;
+    }
+    template <class U> CAVE_DEV U* get_sm(size_t n) {
+        const size_t bytes = (n * sizeof(U) + 15) & ~(size_t)15;
+        U* p = (U*)(sm + sm_front);
+        if (sm_front + bytes <= sm_back) sm_front += bytes; else { hot_overflow = true; overflow = true; }
+        return p;      // callers check `overflow` before touching memory
     }
     template <class U> CAVE_DEV U* get(size_t n) {
-        size_t bytes = (n * sizeof(U) + 15) & ~(size_t)15;
-        if (sm_off + bytes <= sm_cap) { U* p = (U*)(sm + sm_off); sm_off += bytes; return p; }
+        const size_t bytes = (n * sizeof(U) + 15) & ~(size_t)15;
+        if (sm_front + bytes <= sm_back) { sm_back -= bytes; return (U*)(sm + sm_back); }
         if (gl_off + bytes <= gl_cap) { U* p = (U*)(gl + gl_off); gl_off += bytes; return p; }
         overflow = true;
-        return (U*)gl;   // never dereferenced: callers check `overflow` before touching memory
+        return (U*)gl;
+    }
+    template <bool HOT, class U> CAVE_DEV HPtr<U, HOT> geth(size_t n) {
+        if (HOT) return HPtr<U, HOT>(get_sm<U>(n));
+        return HPtr<U, HOT>(get<U>(n));
     }
 };
 
@@ -134,6 +149,115 @@ CAVE_DEV void chol_solve(Ctx& cx, const T* L, int n, int ld, const T* diagL, T* 
     cx.sync();
 }
 
+
+// ------------------------------------------------------------------ blocked LDL^T (Newton systems)
+// In-place LDL^T of the lower triangle of L[0..nf) with unscaled columns (S_ik = l_ik d_k) and one
+// extra row L[nf] holding the right-hand side, which the elimination turns into z = L^-1 g.
+// invd[j] receives 1/d_j.  Panels of 8 columns: warp 0 factors a panel entirely in registers
+// (rows on lanes, shuffles for the pivot column), then all warps apply the rank-8 update to the
+// trailing block — two CTA barriers per panel instead of one or two per column.
+template <class TH, class PL>
+CAVE_DEV void ldlt_blocked(Ctx& cx, PL L, int nf, int ldl, PL invd, TH piv_floor) {
+    constexpr int PB = 8;
+    if (nf + 1 <= 2 * Ctx::WS || Ctx::WS == 1) {
+        for (int j0 = 0; j0 < nf; j0 += PB) {
+            const int pw = nf - j0 < PB ? nf - j0 : PB;
+            if (cx.warp == 0) {
+#ifdef CAVE_HOST_SIM
+                // single-thread restatement of the panel factorisation
+                for (int jj = 0; jj < pw; ++jj) {
+                    const int j = j0 + jj;
+                    TH dj = L[(size_t)j * ldl + j];
+                    const TH inv = (TH)1 / (dj > piv_floor ? dj : piv_floor);
+                    invd[j] = inv;
+                    for (int i = j + 1; i <= nf; ++i) {
+                        const TH f = (TH)L[(size_t)i * ldl + j] * inv;
+                        for (int c = jj + 1; c < pw; ++c)
+                            if (j0 + c <= i || i == nf) L[(size_t)i * ldl + j0 + c] -= f * (TH)L[(size_t)(j0 + c) * ldl + j];
+                    }
+                }
+#else
+                TH a[2][PB];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int i = j0 + cx.lane + 32 * s;
+#pragma unroll
+                    for (int c = 0; c < PB; ++c)
+                        a[s][c] = (i <= nf && c < pw && (j0 + c <= i || i == nf)) ? (TH)L[(size_t)i * ldl + j0 + c] : (TH)0;
+                }
+#pragma unroll
+                for (int jj = 0; jj < PB; ++jj) {
+                    if (jj < pw) {
+                        TH dj = __shfl_sync(0xffffffffu, a[0][jj], jj);
+                        const TH inv = (TH)1 / (dj > piv_floor ? dj : piv_floor);
+                        if (cx.lane == 0) invd[j0 + jj] = inv;
+                        TH pc[PB];
+#pragma unroll
+                        for (int c = jj + 1; c < PB; ++c) pc[c] = __shfl_sync(0xffffffffu, a[0][jj], c);
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) {
+                            const int i = j0 + cx.lane + 32 * s;
+                            if (i > j0 + jj && i <= nf) {
+                                const TH f = a[s][jj] * inv;
+#pragma unroll
+                                for (int c = jj + 1; c < PB; ++c)
+                                    if (c < pw && (j0 + c <= i || i == nf)) a[s][c] -= f * pc[c];
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int i = j0 + cx.lane + 32 * s;
+#pragma unroll
+                    for (int c = 0; c < PB; ++c)
+                        if (i <= nf && c < pw && (j0 + c <= i || i == nf)) L[(size_t)i * ldl + j0 + c] = a[s][c];
+                }
+#endif
+            }
+            cx.sync();
+            // rank-pw update of the trailing block: rows over warps, k over lanes
+            const int t0 = j0 + pw;
+            if (t0 <= nf - 1) {
+                for (int kc = t0; kc <= nf - 1; kc += Ctx::WS) {
+                    const int k = kc + cx.lane;
+                    const bool kin = k <= nf - 1;
+                    TH pk[PB];
+#pragma unroll
+                    for (int c = 0; c < PB; ++c) pk[c] = (kin && c < pw) ? (TH)L[(size_t)k * ldl + j0 + c] * (TH)invd[j0 + c] : (TH)0;
+                    for (int i = kc + cx.warp; i <= nf; i += cx.nwarp) {
+                        const PL li = L + (size_t)i * ldl;
+                        if (kin && (k <= i || i == nf)) {
+                            TH x = li[k];
+                            TH f[PB];
+#pragma unroll
+                            for (int c = 0; c < PB; ++c) f[c] = c < pw ? (TH)li[j0 + c] : (TH)0;
+#pragma unroll
+                            for (int c = 0; c < PB; ++c) x -= f[c] * pk[c];
+                            li[k] = x;
+                        }
+                    }
+                }
+            }
+            cx.sync();
+        }
+        return;
+    }
+    // generic path (nf >= 64): one column at a time
+    for (int j = 0; j < nf; ++j) {
+        cx.sync();
+        TH dj = L[(size_t)j * ldl + j];
+        const TH inv = (TH)1 / (dj > piv_floor ? dj : piv_floor);
+        if (cx.tid == 0) invd[j] = inv;
+        for (int i = j + 1 + cx.warp; i <= nf; i += cx.nwarp) {
+            const TH lij = (TH)L[(size_t)i * ldl + j] * inv;
+            const int kend = i < nf ? i : nf - 1;
+            for (int k = j + 1 + cx.lane; k <= kend; k += Ctx::WS) L[(size_t)i * ldl + k] -= lij * (TH)L[(size_t)k * ldl + j];
+        }
+    }
+    cx.sync();
+}
+
 // ------------------------------------------------------------------ instance description
 struct Instance {
     const float* A;         // this instance's rows, [m_max, d] row-major (global)
@@ -157,49 +281,49 @@ struct Result {
 };
 
 // ------------------------------------------------------------------ Newton path
-template <class T, class TH>
+template <class T, class TH, bool HOT>
 struct NewtonWork {
     int d, mB, nv;
-    T *c, *r, *rt;
-    const uint8_t* ctype;
+    HPtr<T, HOT> c, r, rt;
+    HPtr<uint8_t, HOT> ctype;
     int* rptr; uint16_t* rcol; float* rval;      // CSR of the general rows
     int* grow;                                    // general row -> row index in A
     uint8_t* rtype;                               // 0 bounded, 1 free (merged +-), 2 dropped
     int* vrow;                                    // variable -> CSR row
-    uint8_t* vfree;                               // variable is sign-free
+    HPtr<uint8_t, HOT> vfree;                     // variable is sign-free
     int* cptr; uint16_t* crow; float* cval;      // CSC over variables
-    T *nu, *g, *dir, *nut;
-    int* flist;                                   // free-set variable ids
-    int* fpos;                                    // variable -> position in flist or -1
-    int* cur;                                     // [d] CSC fill cursors, later reused as wflag
-    uint8_t* wflag;                               // [d] psi'(r_k) currently folded into H
-    TH* H;                                        // [nv, nv] lower triangle of B W B^T, kept up to date
-    TH* L;                                        // [(nf+1), ldl] LDL^T work array with the rhs as last row
-    TH* xs;                                       // [nv] Newton step on the free set
+    HPtr<T, HOT> nu, g, dir, nut;
+    HPtr<int, HOT> flist;                         // free-set variable ids
+    HPtr<int, HOT> fpos;                          // variable -> position in flist or -1
+    int* cur;                                     // [d] CSC fill cursors (setup only)
+    HPtr<uint8_t, HOT> wflag;                     // [d] psi'(r_k) currently folded into H
+    HPtr<TH, HOT> H;                              // [nv, nv] lower triangle of B W B^T, kept up to date
+    HPtr<TH, HOT> L;                              // [(nf+1), ldl] LDL^T work array with the rhs as last row
+    HPtr<TH, HOT> xs;                             // [nv] Newton step on the free set, then 1/d_j
 };
 
-template <class T, class TH>
-CAVE_DEV void nw_eval2(Ctx& cx, const NewtonWork<T, TH>& W, const T* nu, T* rout, T& f, T& extra) {
+template <class T, class TH, bool HOT>
+CAVE_DEV void nw_eval2(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> nu, HPtr<T, HOT> rout, T& f, T& extra) {
     T acc = (T)0;
     for (int k = cx.tid; k < W.d; k += cx.nthr) {
         T rk = W.c[k];
-        for (int e = W.cptr[k]; e < W.cptr[k + 1]; ++e) rk -= (T)W.cval[e] * nu[W.crow[e]];
+        for (int e = W.cptr[k]; e < W.cptr[k + 1]; ++e) rk -= (T)W.cval[e] * (T)nu[W.crow[e]];
         rout[k] = rk;
-        T q = psi(rk, (int)W.ctype[k]);
+        T q = psi(rk, (int)(uint8_t)W.ctype[k]);
         acc += q * q;
     }
     cx.block_sum2(acc, extra);
     f = (T)0.5 * acc;
 }
 
-template <class T, class TH>
-CAVE_DEV void nw_grad(Ctx& cx, const NewtonWork<T, TH>& W, const T* r, T* g) {
+template <class T, class TH, bool HOT>
+CAVE_DEV void nw_grad(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> r, HPtr<T, HOT> g) {
     for (int v = cx.warp; v < W.nv; v += cx.nwarp) {
         int row = W.vrow[v];
         T acc = (T)0;
         for (int e = W.rptr[row] + cx.lane; e < W.rptr[row + 1]; e += Ctx::WS) {
             int k = W.rcol[e];
-            acc += (T)W.rval[e] * psi(r[k], (int)W.ctype[k]);
+            acc += (T)W.rval[e] * psi((T)r[k], (int)(uint8_t)W.ctype[k]);
         }
         acc = cx.warp_sum(acc);
         if (cx.lane == 0) g[v] = -acc;
@@ -210,12 +334,12 @@ CAVE_DEV void nw_grad(Ctx& cx, const NewtonWork<T, TH>& W, const T* r, T* g) {
 // Fold the columns whose activity psi'(r_k) changed since the last call into H = B W B^T
 // (lower triangle over ALL variables): H += +-b_k b_k^T with shared-memory atomics.  After the
 // first iterations only a handful of coordinates change sign, so this is almost free.
-template <class T, class TH>
-CAVE_DEV void nw_hessian_update(Ctx& cx, const NewtonWork<T, TH>& W, const T* r) {
+template <class T, class TH, bool HOT>
+CAVE_DEV void nw_hessian_update(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> r) {
     const int nv = W.nv;
     for (int k = cx.tid; k < W.d; k += cx.nthr) {
-        const uint8_t now = psi_active(r[k], (int)W.ctype[k]) ? 1 : 0;
-        if (now == W.wflag[k]) continue;
+        const uint8_t now = psi_active((T)r[k], (int)(uint8_t)W.ctype[k]) ? 1 : 0;
+        if (now == (uint8_t)W.wflag[k]) continue;
         W.wflag[k] = now;
         const TH sg = now ? (TH)1 : (TH)-1;
         const int s = W.cptr[k], e = W.cptr[k + 1];
@@ -225,7 +349,7 @@ CAVE_DEV void nw_hessian_update(Ctx& cx, const NewtonWork<T, TH>& W, const T* r)
             for (int e2 = s; e2 <= e1; ++e2) {
                 const int b = W.crow[e2];
                 const int hi = a > b ? a : b, lo = a > b ? b : a;
-                cx.atomic_addf(&W.H[(size_t)hi * nv + lo], va * (TH)W.cval[e2]);
+                W.H.atomic_add((size_t)hi * nv + lo, va * (TH)W.cval[e2]);
             }
         }
     }
@@ -249,59 +373,58 @@ CAVE_DEV void warp0_inclusive_scan(Ctx& cx, int* x, int n) {
     }
 }
 
-// Bring the CSR of the general rows into the arena (from the scan kernel's pack, or by reading the
-// rows of A when the pack could not hold them), merge +- pairs, build the variable list and the CSC.
-// Returns false (arena overflow) if the instance does not fit the scratch caps.
-template <class T, class TH>
-CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH>& W, T* maxrow_l1, T* maxrow_l2sq) {
+// Setup of one structured instance: merge +- rows, build the variable list, bring the CSR of the kept
+// general rows into the arena (from the scan kernel's pack, or by reading the rows of A when the pack
+// could not hold them) and build the CSC.  HOT selects shared-memory-only allocation for the arrays of
+// the Newton iteration.  Returns false if the instance does not fit (ar.hot_overflow tells which side).
+template <class T, class TH, bool HOT>
+CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH, HOT>& W, T* maxrow_l1, T* maxrow_l2sq) {
     const int d = in.d, mB = in.ngen;
-    W.d = d; W.mB = mB; W.ctype = in.ctype;
-    W.nu = ar.get<T>(mB + 1); W.g = ar.get<T>(mB + 1); W.dir = ar.get<T>(mB + 1); W.nut = ar.get<T>(mB + 1);
+    W.d = d; W.mB = mB;
+    // hot: vectors of the iteration
+    W.nu = ar.geth<HOT, T>(mB + 1); W.g = ar.geth<HOT, T>(mB + 1); W.dir = ar.geth<HOT, T>(mB + 1); W.nut = ar.geth<HOT, T>(mB + 1);
+    W.xs = ar.geth<HOT, TH>(2 * mB + 6);          // Newton step, then reciprocal pivots
+    W.flist = ar.geth<HOT, int>(mB + 2);
+    W.fpos = ar.geth<HOT, int>(mB + 2);
+    W.vfree = ar.geth<HOT, uint8_t>(mB + 1);
+    W.wflag = ar.geth<HOT, uint8_t>(d + 1);
+    HPtr<uint8_t, HOT> ctype_s = ar.geth<HOT, uint8_t>(d + 1);
+    // cold: setup scratch and sparse structure
     W.rptr = ar.get<int>(mB + 2);
+    int* goff = ar.get<int>(mB + 2);              // row offsets in the pack's CSR
     W.grow = ar.get<int>(mB + 1);
     W.rtype = ar.get<uint8_t>(mB + 1);
     W.vrow = ar.get<int>(mB + 1);
-    W.vfree = ar.get<uint8_t>(mB + 1);
-    W.flist = ar.get<int>(mB + 2);
-    W.fpos = ar.get<int>(mB + 2);
     uint64_t* hpos = ar.get<uint64_t>(mB + 1);
     uint64_t* hneg = ar.get<uint64_t>(mB + 1);
     int* cand = ar.get<int>(mB + 1);
-    W.xs = ar.get<TH>(mB + 2);
-    W.cur = ar.get<int>(d + 1);
-    W.wflag = (uint8_t*)W.cur;
     W.cptr = ar.get<int>(d + 2);
-    W.rcol = ar.get<uint16_t>(in.gen_nnz + 8);
-    W.rval = ar.get<float>(in.gen_nnz + 4);
+    W.cur = ar.get<int>(d + 1);
     if (ar.overflow) return false;
-
-    if (cx.tid == 0) W.rptr[0] = 0;
+    cx.phase(1);
+    for (int k = cx.tid; k < d; k += cx.nthr) { ctype_s[k] = in.ctype[k]; W.wflag[k] = 0; }
+    W.ctype = ctype_s;
+    if (cx.tid == 0) { goff[0] = 0; }
     for (int i = cx.tid; i < mB; i += cx.nthr) {
-        gen_t g = in.gen[i]; W.grow[i] = g.x; W.rptr[i + 1] = g.y;
+        gen_t g = in.gen[i]; W.grow[i] = g.x; goff[i + 1] = g.y;
         if (in.csr_ok) { hash_t h = in.ghash[i]; hpos[i] = h.x; hneg[i] = h.y; }
     }
     cx.sync();
-    warp0_inclusive_scan(cx, W.rptr + 1, mB);
-    if (in.csr_ok) {
-        // the scan kernel already compacted the rows: 16-byte copies global -> arena
-#ifdef CAVE_HOST_SIM
-        for (int e = 0; e < in.gen_nnz; ++e) { W.rcol[e] = in.pcol[e]; W.rval[e] = in.pval[e]; }
-#else
-        const int n16c = (in.gen_nnz * 2 + 15) >> 4, n16v = (in.gen_nnz * 4 + 15) >> 4;
-        const uint4* sc = (const uint4*)in.pcol; uint4* dc = (uint4*)W.rcol;
-        const uint4* sv = (const uint4*)in.pval; uint4* dv = (uint4*)W.rval;
-        for (int t = cx.tid; t < n16c; t += cx.nthr) dc[t] = __ldg(sc + t);
-        for (int t = cx.tid; t < n16v; t += cx.nthr) dv[t] = __ldg(sv + t);
-#endif
-        *maxrow_l1 = (T)in.maxl1; *maxrow_l2sq = (T)in.maxl2;
-        cx.sync();
-    } else {
-        cx.sync();
-        // fallback: one warp per row of A, ballot compaction keeps the columns sorted
+    warp0_inclusive_scan(cx, goff + 1, mB);
+    cx.sync();
+    const uint16_t* mcol = in.pcol;     // where the merge verification reads the rows from
+    const float* mval = in.pval;
+    const int* mptr = goff;
+    if (!in.csr_ok) {
+        // fallback: build the CSR of ALL general rows from A (one warp per row, ballot compaction keeps
+        // the columns sorted), computing the hashes and norms the scan kernel could not deliver
+        W.rcol = ar.get<uint16_t>(in.gen_nnz + 8);
+        W.rval = ar.get<float>(in.gen_nnz + 4);
+        if (ar.overflow) return false;
         T l1max = (T)0, l2max = (T)0;
         for (int i = cx.warp; i < mB; i += cx.nwarp) {
             const float* row = in.A + (size_t)W.grow[i] * d;
-            int off = W.rptr[i];
+            int off = goff[i];
             uint64_t hp = 0, hn = 0;
             float l1 = 0.f, l2 = 0.f;
             for (int k0 = 0; k0 < d; k0 += Ctx::WS * 8) {
@@ -336,17 +459,20 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH>
         }
         cx.block_max2(l1max, l2max);    // (barriers inside make the CSR visible)
         *maxrow_l1 = l1max; *maxrow_l2sq = l2max;
+        mcol = W.rcol; mval = W.rval;
+    } else {
+        *maxrow_l1 = (T)in.maxl1; *maxrow_l2sq = (T)in.maxl2;
     }
-
+    cx.phase(2);
     // merge b_j = -b_i : cand[i] = smallest j != i with row_j == -row_i (hash match, then an exact
     // comparison); merged iff the choice is mutual.  One warp per row.
     for (int i = cx.warp; i < mB; i += cx.nwarp) {
-        const int ni = W.rptr[i + 1] - W.rptr[i], pi = W.rptr[i];
+        const int pi = mptr[i], ni = mptr[i + 1] - pi;
         const uint64_t want = hneg[i];
         int c0 = -1;
         for (int j0 = 0; j0 < mB && c0 < 0; j0 += Ctx::WS) {
             const int j = j0 + cx.lane;
-            bool hit = j < mB && j != i && hpos[j] == want && W.rptr[j + 1] - W.rptr[j] == ni;
+            bool hit = j < mB && j != i && hpos[j] == want && mptr[j + 1] - mptr[j] == ni;
             unsigned m = cx.ballot(hit);
             while (m && c0 < 0) {
 #ifdef CAVE_HOST_SIM
@@ -354,10 +480,10 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH>
 #else
                 const int jj = j0 + __ffs(m) - 1;
 #endif
-                const int pj = W.rptr[jj];
+                const int pj = mptr[jj];
                 bool ok = true;
                 for (int e = cx.lane; e < ni; e += Ctx::WS)
-                    ok = ok && W.rcol[pi + e] == W.rcol[pj + e] && W.rval[pi + e] == -W.rval[pj + e];
+                    ok = ok && mcol[pi + e] == mcol[pj + e] && mval[pi + e] == -mval[pj + e];
                 const unsigned bad = cx.ballot(!ok);
                 if (!bad) c0 = jj;
                 m &= m - 1;
@@ -371,7 +497,10 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH>
         W.rtype[i] = (j >= 0 && cand[j] == i) ? (i < j ? 1 : 2) : 0;
     }
     cx.sync();
-    // variables = rows that were not dropped (ordered compaction by warp 0); count CSC entries
+    cx.phase(3);
+    // variables = rows that were not dropped (ordered compaction by warp 0).  With a packed CSR only the
+    // kept rows are copied in (rptr over variables, vrow = identity); in fallback mode the CSR holds every
+    // general row and vrow maps a variable to its row.
     if (cx.warp == 0) {
         int nvb = 0, nz = 0;
         for (int i0 = 0; i0 < mB; i0 += Ctx::WS) {
@@ -380,8 +509,8 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH>
             const unsigned m = cx.ballot(keep);
             if (keep) {
                 const int v = nvb + cx.lanes_below(m);
-                W.vrow[v] = i; W.vfree[v] = W.rtype[i] == 1;
-                nz += W.rptr[i + 1] - W.rptr[i];
+                W.vrow[v] = i; W.vfree[v] = (uint8_t)(W.rtype[i] == 1);
+                nz += goff[i + 1] - goff[i];
             }
             nvb += cx.popc(m);
         }
@@ -393,11 +522,32 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH>
     const int nnzc = W.flist[1];
     cx.sync();
     const int nv = W.nv;
-    W.H = ar.get<TH>((size_t)nv * nv + 1);
-    W.L = ar.get<TH>((size_t)(nv + 1) * ((nv + 1) | 1) + 1);
+    W.H = ar.geth<HOT, TH>((size_t)nv * nv + 1);
+    W.L = ar.geth<HOT, TH>((size_t)(nv + 1) * ((nv + 1) | 1) + 1);
+    if (in.csr_ok) {
+        W.rcol = ar.get<uint16_t>(nnzc + 8);
+        W.rval = ar.get<float>(nnzc + 4);
+    }
     W.crow = ar.get<uint16_t>(nnzc + 1);
     W.cval = ar.get<float>(nnzc + 1);
     if (ar.overflow) return false;
+    if (in.csr_ok) {
+        // rptr over variables, then one warp per kept row copies its non-zeros from the pack
+        if (cx.tid == 0) W.rptr[0] = 0;
+        for (int v = cx.tid; v < nv; v += cx.nthr) { const int i = W.vrow[v]; W.rptr[v + 1] = goff[i + 1] - goff[i]; }
+        cx.sync();
+        warp0_inclusive_scan(cx, W.rptr + 1, nv);
+        cx.sync();
+        for (int v = cx.warp; v < nv; v += cx.nwarp) {
+            const int src = goff[W.vrow[v]], dst = W.rptr[v], n = W.rptr[v + 1] - dst;
+            for (int e = cx.lane; e < n; e += Ctx::WS) { W.rcol[dst + e] = in.pcol[src + e]; W.rval[dst + e] = in.pval[src + e]; }
+        }
+        cx.sync();
+        for (int v = cx.tid; v < nv; v += cx.nthr) W.vrow[v] = v;
+    } else {
+        for (int i = cx.tid; i <= mB; i += cx.nthr) W.rptr[i] = goff[i];
+    }
+    cx.phase(4);
     // CSC: count, scan, fill with a cursor, then order every column by variable id
     for (int k = cx.tid; k <= d; k += cx.nthr) W.cptr[k] = 0;
     for (size_t t = cx.tid; t < (size_t)nv * nv; t += cx.nthr) W.H[t] = (TH)0;
@@ -429,18 +579,16 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH>
             }
     }
     cx.sync();
-    for (int k = cx.tid; k < d; k += cx.nthr) W.wflag[k] = 0;     // (aliases cur: H starts empty)
-    cx.sync();
     return true;
 }
 
-template <class T, class TH>
-CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, T* c, T* r, T* rt, T cnorm,
+template <class T, class TH, bool HOT>
+CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<T, HOT> c, HPtr<T, HOT> r, HPtr<T, HOT> rt, T cnorm,
                            const SolveOpts& opt, Result<T>& out) {
-    NewtonWork<T, TH> W;
+    NewtonWork<T, TH, HOT> W;
     W.c = c; W.r = r; W.rt = rt;
     T l1max, l2max;
-    if (!nw_setup(cx, in, ar, W, &l1max, &l2max)) { out.status = ST_NOSPACE; out.iters = 0; out.r = r; return; }
+    if (!nw_setup<T, TH, HOT>(cx, in, ar, W, &l1max, &l2max)) { out.status = ST_NOSPACE; out.iters = 0; out.r = r.raw(); return; }
     const int nv = W.nv;
     const T scale = (l1max > (T)1 ? l1max : (T)1) * (cnorm > (T)1e-30 ? cnorm : (T)1e-30);
     const T tol = (T)(opt.tol > 0 ? opt.tol : 1e-12) * scale;
@@ -452,28 +600,32 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, T* c, T* r, T
 
     for (int v = cx.tid; v < nv; v += cx.nthr) W.nu[v] = (T)0;
     cx.sync();
-    T *nu = W.nu, *nut = W.nut, *rc = W.r, *rn = W.rt;
+    HPtr<T, HOT> nu = W.nu, nut = W.nut, rc = W.r, rn = W.rt;
+    cx.phase(5);
     T f, dummy = (T)0;
     nw_eval2(cx, W, nu, rc, f, dummy);
     int status = ST_ITER_CAP, it = 0;
     for (; it < max_iter; ++it) {
+        cx.phase(6);
         nw_grad(cx, W, rc, W.g);
         T res = (T)0;
         for (int v = cx.tid; v < nv; v += cx.nthr) {
-            T t = nu[v] - W.g[v];
-            if (!W.vfree[v] && t < (T)0) t = (T)0;
-            T w = cabs(nu[v] - t);
+            const T nv_ = nu[v];
+            T t = nv_ - (T)W.g[v];
+            if (!(uint8_t)W.vfree[v] && t < (T)0) t = (T)0;
+            T w = cabs(nv_ - t);
             res = w > res ? w : res;
         }
         res = cx.block_max(res);
         if (!(res > tol)) { status = ST_CONVERGED; break; }
+        cx.phase(7);
         const T epsb = res < (T)1e-3 ? res : (T)1e-3;
         // ordered free list (every variable that is not epsilon-binding), built by warp 0
         if (cx.warp == 0) {
             int nfb = 0;
             for (int v0 = 0; v0 < nv; v0 += Ctx::WS) {
                 const int v = v0 + cx.lane;
-                const bool isf = v < nv && !(!W.vfree[v] && nu[v] <= epsb && W.g[v] > (T)0);
+                const bool isf = v < nv && !(!(uint8_t)W.vfree[v] && (T)nu[v] <= epsb && (T)W.g[v] > (T)0);
                 const unsigned m = cx.ballot(isf);
                 if (v < nv) {
                     const int pos = nfb + cx.lanes_below(m);
@@ -484,65 +636,40 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, T* c, T* r, T
             }
             if (cx.lane == 0) W.fpos[nv] = nfb;
         }
+        cx.phase(8);
         nw_hessian_update(cx, W, rc);          // (ends with a barrier: flist / fpos visible too)
-        const int nf = W.fpos[nv];
+        const int nf = (int)W.fpos[nv];
         const int ldl = (nf + 1) | 1;
+        cx.phase(9);
         // L <- [H_FF + reg I ; g_F^T]
         for (int a = cx.warp; a <= nf; a += cx.nwarp) {
-            TH* la = W.L + (size_t)a * ldl;
+            const HPtr<TH, HOT> la = W.L + (size_t)a * ldl;
             if (a == nf) {
-                for (int b = cx.lane; b < nf; b += Ctx::WS) la[b] = (TH)W.g[W.flist[b]];
+                for (int b = cx.lane; b < nf; b += Ctx::WS) la[b] = (TH)(T)W.g[(int)W.flist[b]];
             } else {
-                const TH* ha = W.H + (size_t)W.flist[a] * nv;       // flist ascending => flist[a] >= flist[b]
-                for (int b = cx.lane; b <= a; b += Ctx::WS) la[b] = ha[W.flist[b]] + (a == b ? reg : (TH)0);
-            }
-        }
-        // in-place LDL^T, unscaled columns; the rhs row turns into z = L^-1 g   (one barrier per column;
-        // four rows per warp with all loads issued before the stores)
-        for (int j = 0; j < nf; ++j) {
-            cx.sync();
-            TH dj = W.L[(size_t)j * ldl + j];
-            if (!(dj > piv_floor)) dj = piv_floor;
-            const TH inv = (TH)1 / dj;
-            const TH* colj = W.L + j;
-            for (int i0 = j + 1 + cx.warp * 4; i0 <= nf; i0 += cx.nwarp * 4) {
-                TH lij[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) lij[u] = (i0 + u <= nf) ? colj[(size_t)(i0 + u) * ldl] * inv : (TH)0;
-                const int ilast = i0 + 3 < nf ? i0 + 3 : nf;
-                const int kmax = ilast < nf ? ilast : nf - 1;
-                for (int k = j + 1 + cx.lane; k <= kmax; k += Ctx::WS) {
-                    const TH lkj = colj[(size_t)k * ldl];
-                    TH x[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = i0 + u;
-                        x[u] = (i <= nf && (k <= i || i == nf)) ? W.L[(size_t)i * ldl + k] : (TH)0;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = i0 + u;
-                        if (i <= nf && (k <= i || i == nf)) W.L[(size_t)i * ldl + k] = x[u] - lij[u] * lkj;
-                    }
-                }
+                const HPtr<TH, HOT> ha = W.H + (size_t)(int)W.flist[a] * nv;    // flist ascending => flist[a] >= flist[b]
+                for (int b = cx.lane; b <= a; b += Ctx::WS) la[b] = (TH)ha[(int)W.flist[b]] + (a == b ? reg : (TH)0);
             }
         }
         cx.sync();
-        // back substitution D L^T x = z by warp 0 (column oriented, no reductions)
+        cx.phase(10);
+        const HPtr<TH, HOT> invd = W.xs + (nv + 2);
+        ldlt_blocked<TH, HPtr<TH, HOT> >(cx, W.L, nf, ldl, invd, piv_floor);
+        cx.phase(11);
+        // back substitution D L^T x = z by warp 0 (column oriented, no reductions, no divisions)
         if (cx.warp == 0) {
-            TH* z = W.L + (size_t)nf * ldl;
+            const HPtr<TH, HOT> z = W.L + (size_t)nf * ldl;
             for (int j = nf - 1; j >= 0; --j) {
-                TH dj = W.L[(size_t)j * ldl + j];
-                if (!(dj > piv_floor)) dj = piv_floor;
-                const TH xj = z[j] / dj;
+                const TH xj = (TH)z[j] * (TH)invd[j];
                 cx.syncwarp();
                 if (cx.lane == 0) W.xs[j] = xj;
-                for (int i = cx.lane; i < j; i += Ctx::WS) z[i] -= W.L[(size_t)j * ldl + i] * xj;
+                for (int i = cx.lane; i < j; i += Ctx::WS) z[i] -= (TH)W.L[(size_t)j * ldl + i] * xj;
                 cx.syncwarp();
             }
         }
         cx.sync();
-        for (int v = cx.tid; v < nv; v += cx.nthr) W.dir[v] = W.fpos[v] >= 0 ? (T)W.xs[W.fpos[v]] : W.g[v];
+        cx.phase(12);
+        for (int v = cx.tid; v < nv; v += cx.nthr) { const int fp = W.fpos[v]; W.dir[v] = fp >= 0 ? (T)(TH)W.xs[fp] : (T)W.g[v]; }
         cx.sync();
         // Armijo along the projection arc
         T alpha = (T)1, ft = f;
@@ -550,10 +677,11 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, T* c, T* r, T
         for (int ls = 0; ls < max_ls; ++ls) {
             T dec = (T)0;
             for (int v = cx.tid; v < nv; v += cx.nthr) {
-                T t = nu[v] - alpha * W.dir[v];
-                if (!W.vfree[v] && t < (T)0) t = (T)0;
+                const T nv_ = nu[v];
+                T t = nv_ - alpha * (T)W.dir[v];
+                if (!(uint8_t)W.vfree[v] && t < (T)0) t = (T)0;
                 nut[v] = t;
-                dec += W.g[v] * (nu[v] - t);
+                dec += (T)W.g[v] * (nv_ - t);
             }
             cx.sync();
             nw_eval2(cx, W, nut, rn, ft, dec);
@@ -561,11 +689,12 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, T* c, T* r, T
             alpha *= (T)0.5;
         }
         if (!ok) { status = ST_STALLED; break; }
-        T* t1 = nu; nu = nut; nut = t1;
-        T* t2 = rc; rc = rn; rn = t2;
+        HPtr<T, HOT> t1 = nu; nu = nut; nut = t1;
+        HPtr<T, HOT> t2 = rc; rc = rn; rn = t2;
         f = ft;
     }
-    out.r = rc; out.iters = it; out.status = status;
+    cx.phase(13);
+    out.r = rc.raw(); out.iters = it; out.status = status;
 }
 
 // ------------------------------------------------------------------ Lawson-Hanson path (dense rows)
@@ -761,14 +890,14 @@ struct EpiParams {
     double inner_ratio, sign, gscale;   // gscale = 1/B for 'mean', 1 otherwise
 };
 
-template <class T, class TIO>
-CAVE_DEV void epilogue(Ctx& cx, const Instance& in, const EpiParams& ep, const T* c, const T* r,
+template <class T, class TIO, class PC>
+CAVE_DEV void epilogue(Ctx& cx, const Instance& in, const EpiParams& ep, PC c, const T* r,
                        bool have_proj, bool empty_cone, T* tbuf,
                        TIO* grad_out, TIO* proj_out, double* loss_out, double* rnorm_out) {
     const int d = in.d;
     double pp = 0.0, qq = 0.0, cc = 0.0;
     for (int k = cx.tid; k < d; k += cx.nthr) {
-        double ck = (double)c[k];
+        double ck = (double)(T)c[k];
         double q = (have_proj && !empty_cone) ? (double)psi(r[k], (int)in.ctype[k]) : 0.0;
         double p = ck - q;
         pp += p * p; qq += q * q; cc += ck * ck;
@@ -781,7 +910,7 @@ CAVE_DEV void epilogue(Ctx& cx, const Instance& in, const EpiParams& ep, const T
     const bool push = ep.mode == MODE_INNER && !(rnorm < 1e-7);
     double tt = 0.0, ct = 0.0;
     for (int k = cx.tid; k < d; k += cx.nthr) {
-        double ck = (double)c[k], t;
+        double ck = (double)(T)c[k], t;
         if (ep.mode == MODE_HEURISTIC) {
             t = (1.0 - rr) * (ck / cden) + rr * (double)in.avg[k];
         } else {
@@ -801,47 +930,69 @@ CAVE_DEV void epilogue(Ctx& cx, const Instance& in, const EpiParams& ep, const T
     const double gs = ep.gscale * ep.sign;
     for (int k = cx.tid; k < d; k += cx.nthr) {
         double v = (double)tbuf[k] / tden;
-        double w = (double)c[k] * invc;
+        double w = (double)(T)c[k] * invc;
         grad_out[k] = (TIO)(gs * (-(v - cosv * w) / cden));
     }
     if (cx.tid == 0) { *loss_out = 1.0 - cosv; *rnorm_out = (ep.mode == MODE_HEURISTIC) ? 0.0 : rnorm; }
 }
 
 // ------------------------------------------------------------------ one instance, start to finish
-template <class TH, class TIO>
-CAVE_DEV void solve_instance(Ctx& cx, const Instance& in, Arena& ar, const TIO* pred, const EpiParams& ep,
-                             const SolveOpts& opt, TIO* grad_out, TIO* proj_out,
-                             double* loss_out, double* rnorm_out, int* status_out, int* iters_out) {
+template <class TH, class TIO, bool HOT>
+CAVE_DEV bool solve_instance_t(Ctx& cx, const Instance& in, Arena& ar, const TIO* pred, const EpiParams& ep,
+                               const SolveOpts& opt, TIO* grad_out, TIO* proj_out,
+                               double* loss_out, double* rnorm_out, int* status_out, int* iters_out) {
     typedef double T;      // state vectors are always double; TH is the Hessian / factor precision
     const int d = in.d;
-    T* c = ar.get<T>(d); T* r = ar.get<T>(d); T* rt = ar.get<T>(d);
-    if (ar.overflow) {   // cannot even hold the cost vector: report, never a silent number
-        if (cx.tid == 0) { *loss_out = NAN; *rnorm_out = NAN; *status_out = ST_NOSPACE; *iters_out = 0; }
-        for (int k = cx.tid; k < d; k += cx.nthr) { grad_out[k] = (TIO)NAN; if (proj_out) proj_out[k] = (TIO)NAN; }
-        return;
-    }
-    T cc = (T)0;
-    for (int k = cx.tid; k < d; k += cx.nthr) { T v = (T)(ep.sign * (double)pred[k]); c[k] = v; r[k] = v; cc += v * v; }
-    cc = cx.block_sum(cc);
-    const T cnorm = (T)sqrt((double)cc);
-    Result<T> res; res.r = r; res.iters = 0; res.status = ST_SKIPPED;
+    HPtr<T, HOT> c = ar.geth<HOT, T>(d), r = ar.geth<HOT, T>(d), rt = ar.geth<HOT, T>(d);
+    if (HOT && ar.hot_overflow) return false;         // retry with generic placement
+    bool nospace = ar.overflow;                         // cannot even hold the cost vector
+    Result<T> res; res.r = r.raw(); res.iters = 0; res.status = ST_SKIPPED;
     const bool empty = in.nvalid == 0;
-    const bool solve = ep.mode != MODE_HEURISTIC && !empty;
-    if (solve && in.ngen > 0) {
-        if (in.nsingc == 0) lh_solve<T, TH>(cx, in, ar, c, r, cnorm, opt, res);
-        else newton_solve<T, TH>(cx, in, ar, c, r, rt, cnorm, opt, res);
-    } else if (solve) {
-        res.status = ST_CONVERGED;      // only singleton rows: closed form, r = c
+    if (!nospace) {
+        cx.phase(0);
+        T cc = (T)0;
+        for (int k = cx.tid; k < d; k += cx.nthr) { T v = (T)(ep.sign * (double)pred[k]); c[k] = v; r[k] = v; cc += v * v; }
+        cc = cx.block_sum(cc);
+        const T cnorm = (T)sqrt((double)cc);
+        const bool solve = ep.mode != MODE_HEURISTIC && !empty;
+        if (solve && in.ngen > 0) {
+            if (in.nsingc == 0) lh_solve<T, TH>(cx, in, ar, c.raw(), r.raw(), cnorm, opt, res);
+            else newton_solve<T, TH, HOT>(cx, in, ar, c, r, rt, cnorm, opt, res);
+        } else if (solve) {
+            res.status = ST_CONVERGED;      // only singleton rows: closed form, r = c
+        }
+        cx.sync();
+        if ((res.status & 0xff) == ST_NOSPACE) {
+            if (HOT && ar.hot_overflow) return false;   // the shared-memory-only layout did not fit
+            nospace = true;
+        }
     }
-    cx.sync();
-    if ((res.status & 0xff) == ST_NOSPACE) {
-        if (cx.tid == 0) { *loss_out = NAN; *rnorm_out = NAN; *status_out = res.status; *iters_out = 0; }
+    if (nospace) {          // report, never a silent number
+        if (cx.tid == 0) { *loss_out = NAN; *rnorm_out = NAN; *status_out = ST_NOSPACE | (res.status & ST_PATH_LH); *iters_out = 0; }
         for (int k = cx.tid; k < d; k += cx.nthr) { grad_out[k] = (TIO)NAN; if (proj_out) proj_out[k] = (TIO)NAN; }
-        return;
+        return true;
     }
-    T* tbuf = (res.r == r) ? rt : r;
-    epilogue<T, TIO>(cx, in, ep, c, res.r, ep.mode != MODE_HEURISTIC, empty, tbuf, grad_out, proj_out, loss_out, rnorm_out);
+    cx.phase(14);
+    T* tbuf = (res.r == r.raw()) ? rt.raw() : r.raw();
+    epilogue<T, TIO, HPtr<T, HOT> >(cx, in, ep, c, res.r, ep.mode != MODE_HEURISTIC, empty, tbuf, grad_out, proj_out, loss_out, rnorm_out);
     if (cx.tid == 0) { *status_out = res.status; *iters_out = res.iters; }
+    return true;
+}
+
+// One instance, start to finish.  First with the iteration's arrays pinned to shared memory (the
+// fast layout); if they do not fit (very large d or very many general rows) once more with generic
+// placement, where everything may spill to the CTA's global scratch slot.
+template <class TH, class TIO>
+CAVE_DEV void solve_instance(Ctx& cx, const Instance& in, char* smem, size_t smem_bytes, char* slot, size_t slot_bytes,
+                             const TIO* pred, const EpiParams& ep, const SolveOpts& opt, TIO* grad_out, TIO* proj_out,
+                             double* loss_out, double* rnorm_out, int* status_out, int* iters_out) {
+    Arena ar;
+    ar.init(smem, smem_bytes, slot, slot_bytes);
+    if (solve_instance_t<TH, TIO, true>(cx, in, ar, pred, ep, opt, grad_out, proj_out, loss_out, rnorm_out, status_out, iters_out))
+        return;
+    cx.sync();
+    ar.init(smem, smem_bytes, slot, slot_bytes);
+    solve_instance_t<TH, TIO, false>(cx, in, ar, pred, ep, opt, grad_out, proj_out, loss_out, rnorm_out, status_out, iters_out);
 }
 
 }  // namespace cave

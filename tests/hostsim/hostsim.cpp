@@ -61,10 +61,11 @@ static void run(const float* A, int B, int m, int d, const double* pred, double 
         in.csr_ok = (force_path & 2) ? 0 : 1;                                  // bit 1: rebuild the CSR from A
         in.ghash = pk.ghash.data(); in.pcol = pk.col.data(); in.pval = pk.val.data(); in.maxl1 = pk.maxl1; in.maxl2 = pk.maxl2;
         if (force_path & 1) in.nsingc = 0 == in.nsingc ? 1 : in.nsingc;       // bit 0: force the Newton path
-        Arena ar; ar.init(nullptr, 0, buf, cap);
         Ctx cx; EpiParams ep; ep.mode = mode; ep.inner_ratio = inner_ratio; ep.sign = sign; ep.gscale = gscale;
         SolveOpts opt; opt.max_iter = 0; opt.max_ls = 0; opt.tol = 0;
-        solve_instance<T, double>(cx, in, ar, pred + (size_t)b * d, ep, opt, grad + (size_t)b * d, proj + (size_t)b * d,
+        // a small "shared memory" so that both placements (shared-only hot arrays / generic) get exercised
+        static char fake_smem[96 * 1024];
+        solve_instance<T, double>(cx, in, fake_smem, sizeof(fake_smem), buf, cap, pred + (size_t)b * d, ep, opt, grad + (size_t)b * d, proj + (size_t)b * d,
                                   loss_i + b, rnorm + b, status + b, iters + b);
     }
     free(buf);

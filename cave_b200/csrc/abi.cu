@@ -114,7 +114,7 @@ int cave_pack(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, i
     p.A = A; p.m_rows = m_rows; p.B = (int)B; p.m_max = (int)m_max; p.d = (int)d; p.dpad = L.dpad;
     p.nvalid = (int*)(base + L.nvalid); p.navg = (int*)(base + L.navg); p.ngen = (int*)(base + L.ngen);
     p.gennnz = (int*)(base + L.gennnz); p.nsingc = (int*)(base + L.nsingc);
-    p.gen = (int2*)(base + L.gen); p.ctype = (unsigned char*)(base + L.ctype); p.avg = (float*)(base + L.avg);
+    p.gen4 = (int4*)(base + L.gen); p.ctype = (unsigned char*)(base + L.ctype); p.avg = (float*)(base + L.avg);
     p.ghash = (ulonglong2*)(base + L.ghash); p.csr_col = (uint16_t*)(base + L.csr_col); p.csr_val = (float*)(base + L.csr_val);
     p.cap_nnz = (int)L.cap_nnz; p.csr_ok = (int*)(base + L.csrok); p.maxl1 = (float*)(base + L.maxl1); p.maxl2 = (float*)(base + L.maxl2);
     cudaError_t e = cave::launch_scan(p, (cudaStream_t)stream);
@@ -162,7 +162,7 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     sp.B = (int)B; sp.m_max = (int)m_max; sp.d = (int)d; sp.dpad = PL.dpad;
     sp.nvalid = (const int*)(pb + PL.nvalid); sp.ngen = (const int*)(pb + PL.ngen);
     sp.gennnz = (const int*)(pb + PL.gennnz); sp.nsingc = (const int*)(pb + PL.nsingc);
-    sp.gen = (const int2*)(pb + PL.gen); sp.ctype = (const unsigned char*)(pb + PL.ctype); sp.avg = (const float*)(pb + PL.avg);
+    sp.gen = (const int4*)(pb + PL.gen); sp.ctype = (const unsigned char*)(pb + PL.ctype); sp.avg = (const float*)(pb + PL.avg);
     sp.csr_ok = (const int*)(pb + PL.csrok); sp.maxl1 = (const float*)(pb + PL.maxl1); sp.maxl2 = (const float*)(pb + PL.maxl2);
     sp.ghash = (const ulonglong2*)(pb + PL.ghash); sp.csr_col = (const uint16_t*)(pb + PL.csr_col);
     sp.csr_val = (const float*)(pb + PL.csr_val); sp.cap_nnz = PL.cap_nnz;

@@ -19,11 +19,12 @@ CAVE_HD size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 //   ngen[B]     valid rows with >= 2 non-zeros     ("general" rows)
 //   gennnz[B]   non-zeros in the general rows
 //   nsingc[B]   coordinates that own at least one singleton row
-//   gen[B, m_max]   (row index, nnz) of every general row, ascending
+//   gen[B, m_max]   int4 (row index, nnz, offset into the packed CSR, 0) of every general row, ascending row
+//                   (offsets need not be monotone: rows are placed as they are scanned)
 //   ctype[B, dpad]  per coordinate: bit0 = a row +a*e_k exists, bit1 = a row -a*e_k exists
 //   avg[B, dpad]    float32 average unit normal     (src/cave.py:222-228)
 //   csrok[B], maxl1[B], maxl2[B]   packed-CSR complete flag; max ||a||_1, max ||a||_2^2 over general rows
-//   ghash[B, m_max]   per general row: order-free 64-bit hashes of the row and of its negation
+//   ghash[B, m_max]   indexed by ROW: order-free 64-bit hashes of the row and of its negation (general rows only)
 //   csr_col/val[B, cap_nnz]   the general rows' non-zeros, row after row, columns ascending
 struct PackLayout {
     size_t nvalid, navg, ngen, gennnz, nsingc, gen, ctype, avg, csrok, maxl1, maxl2, ghash, csr_col, csr_val, total;
@@ -46,7 +47,7 @@ CAVE_HD PackLayout make_pack_layout(int64_t B, int64_t m_max, int64_t d) {
     L.ngen = o;   o = align_up(o + (size_t)B * 4, 256);
     L.gennnz = o; o = align_up(o + (size_t)B * 4, 256);
     L.nsingc = o; o = align_up(o + (size_t)B * 4, 256);
-    L.gen = o;    o = align_up(o + (size_t)B * (size_t)m_max * 8, 256);
+    L.gen = o;    o = align_up(o + (size_t)B * (size_t)m_max * 16, 256);
     L.ctype = o;  o = align_up(o + (size_t)B * (size_t)L.dpad, 256);
     L.avg = o;    o = align_up(o + (size_t)B * (size_t)L.dpad * 4, 256);
     L.cap_nnz = pack_cap_nnz(m_max, d);

@@ -15,6 +15,7 @@
 // All accumulation orders are fixed, so the pack is bit-reproducible run to run.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "layout.cuh"
 #include "scan_kernel.cuh"
 
@@ -114,8 +115,8 @@ __global__ void __launch_bounds__(NT) scan_kernel(ScanParams p) {
     // bookkeeper-only counters (thread NT-1)
     int c_nvalid = 0, c_navg = 0;
     int overflow = 0;
-    int2* gen_out = p.gen + (size_t)b * p.m_max;
-    ulonglong2* hash_out = p.ghash + (size_t)b * p.m_max;
+    int4* gen_out = p.gen4 + (size_t)b * p.m_max;
+    ulonglong2* hash_out = p.ghash + (size_t)b * p.m_max;      // row-indexed
     uint16_t* col_out = p.csr_col + (size_t)b * p.cap_nnz;
     float* val_out = p.csr_val + (size_t)b * p.cap_nnz;
 
@@ -253,8 +254,8 @@ __global__ void __launch_bounds__(NT) scan_kernel(ScanParams p) {
                         }
                     }
                     if (lane == 0) {
-                        gen_out[t_ngen + ord] = make_int2(t * R + rr, cnt);
-                        hash_out[t_ngen + ord] = make_ulonglong2(hp, hn);
+                        gen_out[t_ngen + ord] = make_int4(t * R + rr, cnt, off, 0);
+                        hash_out[t * R + rr] = make_ulonglong2(hp, hn);
                     }
                 }
                 if (off + cnt > p.cap_nnz) overflow = 1;
@@ -290,6 +291,261 @@ __global__ void __launch_bounds__(NT) scan_kernel(ScanParams p) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Warp-streaming variant (rows up to a few KB: every shipped model).  No CTA barrier in the steady
+// state: warp w owns rows w, w+8, ... of the instance and a private ring of row buffers that its lane 0
+// refills with TMA bulk copies, so eight independent row streams are in flight per CTA.  Cross-row
+// state is either warp-private (fixed order => reproducible) or exact under reordering (integer
+// atomics); the ordered general-row list is assembled once per instance after a single barrier.
+template <int NT, int S>
+__global__ void __launch_bounds__(NT) scan_rows_kernel(ScanParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+    const int d = p.d;
+    const int b = blockIdx.x;
+    const size_t rowbuf = p.stage_stride;
+
+    unsigned char* ring = smem;                                             // [NW][S][rowbuf]
+    float* avg_w = (float*)(smem + (size_t)NW * S * rowbuf);                // [NW][d]
+    int* sing = (int*)(avg_w + (size_t)NW * d);                             // [d]
+    int2* rowinfo = (int2*)align_up((size_t)(sing + d), 8);                 // [m_max] (cnt, off); cnt = 0: not general
+    uint64_t* full = (uint64_t*)(rowinfo + p.m_max);                        // [NW*S]
+    int* s_cnt = (int*)(full + NW * S);                                     // [16]
+    float* s_max = (float*)(s_cnt + 16);                                    // [2*NW]
+    unsigned* ctype_w = (unsigned*)align_up((size_t)(s_max + 2 * NW), 16);  // [dpad/4] words of 4 cone types
+
+    const int m_b = p.m_rows ? min(max(p.m_rows[b], 0), p.m_max) : p.m_max;
+    const float* A_b = p.A + (size_t)b * p.m_max * d;
+
+    for (int k = tid; k < NW * d; k += NT) avg_w[k] = 0.f;
+    for (int k = tid; k < d; k += NT) sing[k] = 0;
+    for (int k = tid; k < (int)(p.dpad / 4); k += NT) ctype_w[k] = 0u;
+    for (int k = tid; k < p.m_max; k += NT) rowinfo[k] = make_int2(0, 0);
+    if (tid < 16) s_cnt[tid] = 0;
+    if (tid == 0) {
+        for (int i = 0; i < NW * S; ++i) mbar_init(full + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    unsigned char* myring = ring + (size_t)warp * S * rowbuf;
+    uint64_t* mybar = full + warp * S;
+    auto issue = [&](int it) {          // lane 0 only
+        const int s = it % S;
+        const int row = warp + NW * it;
+        const uintptr_t a = (uintptr_t)(A_b + (size_t)row * d);
+        const uintptr_t a0 = a & ~(uintptr_t)15;
+        const uintptr_t a1 = (a + (size_t)d * 4 + 15) & ~(uintptr_t)15;
+        const uint32_t bytes = (uint32_t)(a1 - a0);
+        mbar_expect_tx(mybar + s, bytes);
+        tma_bulk_g2s(myring + (size_t)s * rowbuf, (const void*)a0, bytes, mybar + s);
+    };
+    const int nit = m_b > warp ? (m_b - warp + NW - 1) / NW : 0;
+    if (lane == 0)
+        for (int it = 0; it < S && it < nit; ++it) issue(it);
+
+    int w_nvalid = 0, w_navg = 0, w_gennnz = 0, w_ngen = 0;
+    float w_l1max = 0.f, w_l2max = 0.f;
+    float* myavg = avg_w + (size_t)warp * d;
+    uint16_t* col_out = p.csr_col + (size_t)b * p.cap_nnz;
+    float* val_out = p.csr_val + (size_t)b * p.cap_nnz;
+    ulonglong2* hash_out = p.ghash + (size_t)b * p.m_max;       // row-indexed
+
+    for (int it = 0; it < nit; ++it) {
+        const int s = it % S;
+        const int row_id = warp + NW * it;
+        const uintptr_t a = (uintptr_t)(A_b + (size_t)row_id * d);
+        const int shift = (int)((a & 15) >> 2);
+        const float* base = (const float*)(myring + (size_t)s * rowbuf);
+        mbar_wait(mybar + s, (uint32_t)((it / S) & 1));
+
+        const int e0 = shift, e1 = e0 + d;
+        const int q0 = (e0 + 3) >> 2, q1 = e1 >> 2;
+        RowAcc acc; acc.l1 = 0.f; acc.l2 = 0.f; acc.lv = 0.f; acc.lk = -1; acc.n = 0;
+        if (q0 <= q1) {
+            if (lane < 4) {
+                const int kh = e0 + lane;
+                if (kh < (q0 << 2) && kh < e1) { float v = base[kh]; if (v != 0.f) acc.add(v, kh - e0); }
+                const int kt = (q1 << 2) + lane;
+                if (kt >= (q0 << 2) && kt < e1) { float v = base[kt]; if (v != 0.f) acc.add(v, kt - e0); }
+            }
+            const float4* b4 = (const float4*)base;
+            for (int q = q0 + lane; q < q1 + lane; q += 64) {       // two independent words per trip
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                if (q < q1) v0 = b4[q];
+                if (q + 32 < q1) v1 = b4[q + 32];
+                const uint32_t any0 = (__float_as_uint(v0.x) | __float_as_uint(v0.y) | __float_as_uint(v0.z) | __float_as_uint(v0.w)) << 1;
+                const uint32_t any1 = (__float_as_uint(v1.x) | __float_as_uint(v1.y) | __float_as_uint(v1.z) | __float_as_uint(v1.w)) << 1;
+                if (__ballot_sync(0xffffffffu, (any0 | any1) != 0u) == 0u) continue;
+                if (any0 != 0u) {
+                    const int k = (q << 2) - e0;
+                    if (v0.x != 0.f) acc.add(v0.x, k);
+                    if (v0.y != 0.f) acc.add(v0.y, k + 1);
+                    if (v0.z != 0.f) acc.add(v0.z, k + 2);
+                    if (v0.w != 0.f) acc.add(v0.w, k + 3);
+                }
+                if (any1 != 0u) {
+                    const int k = ((q + 32) << 2) - e0;
+                    if (v1.x != 0.f) acc.add(v1.x, k);
+                    if (v1.y != 0.f) acc.add(v1.y, k + 1);
+                    if (v1.z != 0.f) acc.add(v1.z, k + 2);
+                    if (v1.w != 0.f) acc.add(v1.w, k + 3);
+                }
+            }
+        } else {
+            for (int k = e0 + lane; k < e1; k += 32) { float v = base[k]; if (v != 0.f) acc.add(v, k - e0); }
+        }
+        int cnt = 0;
+        const unsigned sawm = __ballot_sync(0xffffffffu, acc.n > 0);
+        if (sawm) {
+            if ((sawm & (sawm - 1)) == 0u) {
+                cnt = __shfl_sync(0xffffffffu, acc.n, __ffs(sawm) - 1);
+            } else {
+                cnt = acc.n;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            }
+        }
+        if (cnt == 1) {
+            const int src = __ffs(sawm) - 1;
+            const int k1 = __shfl_sync(0xffffffffu, acc.lk, src);
+            const float v1 = __shfl_sync(0xffffffffu, acc.lv, src);
+            const bool nv = fabsf(v1) > 1e-7f, av = sqrtf(v1 * v1) > 1e-7f;
+            w_nvalid += nv; w_navg += av;
+            if (lane == 0) {
+                if (nv) atomicOr(&ctype_w[k1 >> 2], (v1 > 0.f ? 1u : 2u) << ((k1 & 3) * 8));
+                if (av) atomicAdd(&sing[k1], v1 > 0.f ? 1 : -1);
+            }
+        } else if (cnt >= 2) {
+            float a1 = acc.l1, a2 = acc.l2;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+            }
+            const float nrm = sqrtf(a2);
+            const bool nv = a1 > 1e-7f, av = nrm > 1e-7f;
+            const float inv = av ? 1.f / fmaxf(nrm, 1e-8f) : 0.f;
+            w_nvalid += nv; w_navg += av;
+            int off = 0;
+            bool fits = false;
+            if (nv) {
+                if (lane == 0) off = atomicAdd(&s_cnt[5], cnt);
+                off = __shfl_sync(0xffffffffu, off, 0);
+                fits = off + cnt <= p.cap_nnz;
+                if (!fits && lane == 0) s_cnt[6] = 1;
+                w_gennnz += cnt; ++w_ngen;
+                w_l1max = fmaxf(w_l1max, a1); w_l2max = fmaxf(w_l2max, a2);
+            }
+            uint64_t hp = 0, hn = 0;
+            const float* row = base + shift;
+            int w = off;
+            for (int k0 = 0; k0 < d; k0 += 32) {
+                const int k = k0 + lane;
+                const float v = k < d ? row[k] : 0.f;
+                const unsigned nzm = __ballot_sync(0xffffffffu, v != 0.f);
+                if (v != 0.f) {
+                    if (av) myavg[k] = fmaf(v, inv, myavg[k]);
+                    if (fits) {
+                        const int pos = w + __popc(nzm & ((1u << lane) - 1u));
+                        col_out[pos] = (uint16_t)k; val_out[pos] = v;
+                        const uint32_t bits = __float_as_uint(v);
+                        hp += mix64d(((uint64_t)k << 32) | bits);
+                        hn += mix64d(((uint64_t)k << 32) | (bits ^ 0x80000000u));
+                    }
+                }
+                w += __popc(nzm);
+            }
+            if (nv) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    hp += __shfl_xor_sync(0xffffffffu, hp, o);
+                    hn += __shfl_xor_sync(0xffffffffu, hn, o);
+                }
+                if (lane == 0) {
+                    rowinfo[row_id] = make_int2(cnt, off);
+                    hash_out[row_id] = make_ulonglong2(hp, hn);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && it + S < nit) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(it + S);
+        }
+    }
+
+    // ---- once per instance: totals and the ordered general-row list
+    if (lane == 0) {
+        atomicAdd(&s_cnt[0], w_nvalid); atomicAdd(&s_cnt[1], w_navg);
+        atomicAdd(&s_cnt[2], w_ngen); atomicAdd(&s_cnt[3], w_gennnz);
+        s_max[warp] = w_l1max; s_max[NW + warp] = w_l2max;
+    }
+    __syncthreads();
+    {   // rows are split into NW contiguous chunks; warp-ballot compaction inside, chunk bases via s_cnt[8..]
+        const int chunk = (p.m_max + NW - 1) / NW;
+        const int r0 = warp * chunk, r1 = min(r0 + chunk, p.m_max);
+        int mine = 0;
+        for (int r = r0 + lane; r < r1 + lane; r += 32) {
+            const bool g = r < r1 && rowinfo[r].x > 0;
+            mine += __popc(__ballot_sync(0xffffffffu, g));
+        }
+        if (lane == 0) s_cnt[8 + warp] = mine;
+        __syncthreads();
+        int basei = 0;
+        for (int w2 = 0; w2 < warp; ++w2) basei += s_cnt[8 + w2];
+        int4* gen_out = p.gen4 + (size_t)b * p.m_max;
+        for (int r = r0 + lane; r < r1 + lane; r += 32) {
+            const bool g = r < r1 && rowinfo[r].x > 0;
+            const unsigned m = __ballot_sync(0xffffffffu, g);
+            if (g) {
+                const int2 ri = rowinfo[r];
+                gen_out[basei + __popc(m & ((1u << lane) - 1u))] = make_int4(r, ri.x, ri.y, 0);
+            }
+            basei += __popc(m);
+        }
+    }
+    int nsc = 0;
+    for (int k = tid; k < (int)(p.dpad / 4); k += NT) {
+        const unsigned wv = ctype_w[k];
+        nsc += ((wv & 0xffu) != 0) + ((wv & 0xff00u) != 0) + ((wv & 0xff0000u) != 0) + ((wv & 0xff000000u) != 0);
+    }
+    for (int o = 16; o > 0; o >>= 1) nsc += __shfl_xor_sync(0xffffffffu, nsc, o);
+    if (lane == 0 && nsc) atomicAdd(&s_cnt[4], nsc);
+    __syncthreads();
+    const float ninv = 1.f / (float)max(s_cnt[1], 1);
+    float* avg_out = p.avg + (size_t)b * p.dpad;
+    for (int k = tid; k < (int)p.dpad; k += NT) {
+        float acc = 0.f;
+        if (k < d) {
+#pragma unroll
+            for (int w2 = 0; w2 < NW; ++w2) acc += avg_w[(size_t)w2 * d + k];
+            acc = (acc + (float)sing[k]) * ninv;
+        }
+        avg_out[k] = acc;
+    }
+    uint32_t* ct_out = (uint32_t*)(p.ctype + (size_t)b * p.dpad);
+    for (int k = tid; k < (int)(p.dpad / 4); k += NT) ct_out[k] = ctype_w[k];
+    if (tid == 0) {
+        float m1 = 0.f, m2 = 0.f;
+        for (int w2 = 0; w2 < NW; ++w2) { m1 = fmaxf(m1, s_max[w2]); m2 = fmaxf(m2, s_max[NW + w2]); }
+        p.nvalid[b] = s_cnt[0]; p.navg[b] = s_cnt[1]; p.ngen[b] = s_cnt[2]; p.gennnz[b] = s_cnt[3]; p.nsingc[b] = s_cnt[4];
+        p.csr_ok[b] = s_cnt[6] ? 0 : 1;
+        p.maxl1[b] = m1; p.maxl2[b] = m2;
+    }
+}
+
+size_t scan_rows_smem_bytes(int d, int m_max, int NW, int S, size_t* rowbuf_out) {
+    const size_t rowbuf = align_up((size_t)d * 4 + 32, 128);
+    const int64_t dpad = (int64_t)align_up((size_t)d, 16);
+    size_t o = (size_t)NW * S * rowbuf + (size_t)NW * d * 4 + (size_t)d * 4 + 8;
+    o += (size_t)m_max * 8 + (size_t)NW * S * 8 + 16 * 4 + 2 * NW * 4 + 16 + (size_t)dpad;
+    if (rowbuf_out) *rowbuf_out = rowbuf;
+    return align_up(o, 16);
+}
+
 size_t scan_smem_bytes(int d, int R, int stages, size_t* stage_stride_out) {
     const size_t stride = align_up((size_t)R * d * 4 + 32, 128);
     const int64_t dpad = (int64_t)align_up((size_t)d, 16);
@@ -306,6 +562,22 @@ size_t scan_smem_bytes(int d, int R, int stages, size_t* stage_stride_out) {
 cudaError_t launch_scan(const ScanParams& p0, cudaStream_t stream) {
     ScanParams p = p0;
     constexpr int NT = 256;
+    {   // warp-streaming kernel whenever eight 3-deep row rings fit in shared memory
+        size_t rowbuf = 0;
+        const size_t smem = scan_rows_smem_bytes(p.d, p.m_max, NT / 32, 3, &rowbuf);
+        const char* force = getenv("CAVE_SCAN_KERNEL");
+        if (smem <= 220 * 1024 && !(force && force[0] == 't')) {
+            p.stage_stride = rowbuf; p.R = 1; p.stages = 3;
+            static size_t configured_rows = 0;
+            if (smem > configured_rows) {
+                cudaError_t e = cudaFuncSetAttribute(scan_rows_kernel<NT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                configured_rows = smem;
+            }
+            scan_rows_kernel<NT, 3><<<dim3((unsigned)p.B), dim3(NT), smem, stream>>>(p);
+            return cudaGetLastError();
+        }
+    }
     // tile = R rows, about 20 KB; ring depth 4 unless shared memory runs out
     int R = (int)(20480 / ((size_t)p.d * 4));
     R = R < 1 ? 1 : (R > 32 ? 32 : R);

@@ -12,7 +12,7 @@ struct ScanParams {
     size_t stage_stride;    // filled by launch_scan
     int64_t dpad;
     int *nvalid, *navg, *ngen, *gennnz, *nsingc;
-    int2* gen;
+    int4* gen4;             // per general row: (row, nnz, offset in the packed CSR, 0), ascending row
     unsigned char* ctype;
     float* avg;
     // packed CSR of the general rows (per instance capacity cap_nnz) + row hashes for +-row matching

@@ -13,7 +13,7 @@ struct SolveParams {
     int64_t dpad;
     // pack
     const int *nvalid, *ngen, *gennnz, *nsingc;
-    const int2* gen;
+    const int4* gen;
     const unsigned char* ctype;
     const float* avg;
     const int* csr_ok;

@@ -26,14 +26,14 @@
 namespace cave {
 
 #ifdef CAVE_HOST_SIM
-struct int2_ { int x, y; };
-typedef int2_ gen_t;
+struct int4_ { int x, y, z, w; };
+typedef int4_ gen_t;
 struct u64x2_ { uint64_t x, y; };
 typedef u64x2_ hash_t;
 struct float4_ { float x, y, z, w; };
 typedef float4_ f4_t;
 #else
-typedef int2 gen_t;
+typedef int4 gen_t;
 typedef float4 f4_t;
 typedef ulonglong2 hash_t;
 #endif
@@ -261,13 +261,13 @@ CAVE_DEV void ldlt_blocked(Ctx& cx, PL L, int nf, int ldl, PL invd, TH piv_floor
 // ------------------------------------------------------------------ instance description
 struct Instance {
     const float* A;         // this instance's rows, [m_max, d] row-major (global)
-    const gen_t* gen;       // general rows: (row index, nnz), ascending row   (from the pack)
+    const gen_t* gen;       // general rows: (row index, nnz, offset in the packed CSR, 0), ascending row
     const uint8_t* ctype;   // [d] singleton cone type per coordinate            (from the pack)
     const float* avg;       // [d] average unit normal (src/cave.py:222-228)     (from the pack)
     int d, ngen, gen_nnz, nvalid, nsingc;
     // packed CSR of the general rows written by the scan kernel (valid iff csr_ok)
     int csr_ok;
-    const hash_t* ghash;    // per general row: hash(row), hash(-row)
+    const hash_t* ghash;    // indexed by row: hash(row), hash(-row)   (general rows only)
     const uint16_t* pcol;
     const float* pval;
     float maxl1, maxl2;     // max ||a_i||_1, max ||a_i||_2^2 over the general rows
@@ -391,7 +391,8 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     HPtr<uint8_t, HOT> ctype_s = ar.geth<HOT, uint8_t>(d + 1);
     // cold: setup scratch and sparse structure
     W.rptr = ar.get<int>(mB + 2);
-    int* goff = ar.get<int>(mB + 2);              // row offsets in the pack's CSR
+    int* goff = ar.get<int>(mB + 2);              // row offsets in the source CSR (pack, or the one built here)
+    int* gcnt = ar.get<int>(mB + 2);              // non-zeros per general row
     W.grow = ar.get<int>(mB + 1);
     W.rtype = ar.get<uint8_t>(mB + 1);
     W.vrow = ar.get<int>(mB + 1);
@@ -404,18 +405,20 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     cx.phase(1);
     for (int k = cx.tid; k < d; k += cx.nthr) { ctype_s[k] = in.ctype[k]; W.wflag[k] = 0; }
     W.ctype = ctype_s;
-    if (cx.tid == 0) { goff[0] = 0; }
     for (int i = cx.tid; i < mB; i += cx.nthr) {
-        gen_t g = in.gen[i]; W.grow[i] = g.x; goff[i + 1] = g.y;
-        if (in.csr_ok) { hash_t h = in.ghash[i]; hpos[i] = h.x; hneg[i] = h.y; }
+        gen_t g = in.gen[i]; W.grow[i] = g.x; gcnt[i] = g.y; goff[i] = g.z;
+        if (in.csr_ok) { hash_t h = in.ghash[g.x]; hpos[i] = h.x; hneg[i] = h.y; }
     }
-    cx.sync();
-    warp0_inclusive_scan(cx, goff + 1, mB);
     cx.sync();
     const uint16_t* mcol = in.pcol;     // where the merge verification reads the rows from
     const float* mval = in.pval;
-    const int* mptr = goff;
     if (!in.csr_ok) {
+        // offsets of the CSR built here = exclusive scan of the counts
+        if (cx.tid == 0) goff[0] = 0;
+        for (int i = cx.tid; i < mB; i += cx.nthr) goff[i + 1] = gcnt[i];
+        cx.sync();
+        warp0_inclusive_scan(cx, goff + 1, mB);
+        cx.sync();
         // fallback: build the CSR of ALL general rows from A (one warp per row, ballot compaction keeps
         // the columns sorted), computing the hashes and norms the scan kernel could not deliver
         W.rcol = ar.get<uint16_t>(in.gen_nnz + 8);
@@ -467,12 +470,12 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     // merge b_j = -b_i : cand[i] = smallest j != i with row_j == -row_i (hash match, then an exact
     // comparison); merged iff the choice is mutual.  One warp per row.
     for (int i = cx.warp; i < mB; i += cx.nwarp) {
-        const int pi = mptr[i], ni = mptr[i + 1] - pi;
+        const int pi = goff[i], ni = gcnt[i];
         const uint64_t want = hneg[i];
         int c0 = -1;
         for (int j0 = 0; j0 < mB && c0 < 0; j0 += Ctx::WS) {
             const int j = j0 + cx.lane;
-            bool hit = j < mB && j != i && hpos[j] == want && mptr[j + 1] - mptr[j] == ni;
+            bool hit = j < mB && j != i && hpos[j] == want && gcnt[j] == ni;
             unsigned m = cx.ballot(hit);
             while (m && c0 < 0) {
 #ifdef CAVE_HOST_SIM
@@ -480,7 +483,7 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
 #else
                 const int jj = j0 + __ffs(m) - 1;
 #endif
-                const int pj = mptr[jj];
+                const int pj = goff[jj];
                 bool ok = true;
                 for (int e = cx.lane; e < ni; e += Ctx::WS)
                     ok = ok && mcol[pi + e] == mcol[pj + e] && mval[pi + e] == -mval[pj + e];
@@ -510,7 +513,7 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
             if (keep) {
                 const int v = nvb + cx.lanes_below(m);
                 W.vrow[v] = i; W.vfree[v] = (uint8_t)(W.rtype[i] == 1);
-                nz += goff[i + 1] - goff[i];
+                nz += gcnt[i];
             }
             nvb += cx.popc(m);
         }
@@ -534,7 +537,7 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     if (in.csr_ok) {
         // rptr over variables, then one warp per kept row copies its non-zeros from the pack
         if (cx.tid == 0) W.rptr[0] = 0;
-        for (int v = cx.tid; v < nv; v += cx.nthr) { const int i = W.vrow[v]; W.rptr[v + 1] = goff[i + 1] - goff[i]; }
+        for (int v = cx.tid; v < nv; v += cx.nthr) W.rptr[v + 1] = gcnt[W.vrow[v]];
         cx.sync();
         warp0_inclusive_scan(cx, W.rptr + 1, nv);
         cx.sync();
@@ -545,7 +548,8 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
         cx.sync();
         for (int v = cx.tid; v < nv; v += cx.nthr) W.vrow[v] = v;
     } else {
-        for (int i = cx.tid; i <= mB; i += cx.nthr) W.rptr[i] = goff[i];
+        for (int i = cx.tid; i < mB; i += cx.nthr) W.rptr[i] = goff[i];
+        if (cx.tid == 0) W.rptr[mB] = goff[mB - 1] + gcnt[mB - 1];
     }
     cx.phase(4);
     // CSC: count, scan, fill with a cursor, then order every column by variable id

@@ -16,7 +16,7 @@ struct HostPack {
     float maxl1 = 0.f, maxl2 = 0.f;
 };
 static void host_pack(const float* A, int m, int d, HostPack& pk) {
-    pk.ctype.assign(d, 0); pk.avg.assign(d, 0.f);
+    pk.ctype.assign(d, 0); pk.avg.assign(d, 0.f); pk.ghash.assign(m, hash_t{0, 0});
     std::vector<float> gen_acc(d, 0.f); std::vector<int> sing(d, 0);
     for (int i = 0; i < m; ++i) {
         const float* row = A + (size_t)i * d;
@@ -31,14 +31,14 @@ static void host_pack(const float* A, int m, int d, HostPack& pk) {
             if (av) sing[lk] += lv > 0.f ? 1 : -1;
         } else if (cnt >= 2) {
             if (nv) {
-                gen_t g; g.x = i; g.y = cnt; pk.gen.push_back(g); pk.gen_nnz += cnt;
+                gen_t g; g.x = i; g.y = cnt; g.z = pk.gen_nnz; g.w = 0; pk.gen.push_back(g); pk.gen_nnz += cnt;
                 hash_t h; h.x = 0; h.y = 0;
                 for (int k = 0; k < d; ++k) if (row[k] != 0.f) {
                     union { float f; uint32_t u; } cv; cv.f = row[k];
                     h.x += mix64(((uint64_t)k << 32) | cv.u); h.y += mix64(((uint64_t)k << 32) | (cv.u ^ 0x80000000u));
                     pk.col.push_back((uint16_t)k); pk.val.push_back(row[k]);
                 }
-                pk.ghash.push_back(h);
+                pk.ghash[i] = h;
                 pk.maxl1 = fmaxf(pk.maxl1, l1); pk.maxl2 = fmaxf(pk.maxl2, nrm * nrm);
             }
             if (av) for (int k = 0; k < d; ++k) gen_acc[k] += row[k] * inv;

@@ -308,8 +308,10 @@ __global__ void __launch_bounds__(NT) scan_rows_kernel(ScanParams p) {
     const size_t rowbuf = p.stage_stride;
 
     unsigned char* ring = smem;                                             // [NW][S][rowbuf]
-    float* avg_w = (float*)(smem + (size_t)NW * S * rowbuf);                // [NW][d]
-    int* sing = (int*)(avg_w + (size_t)NW * d);                             // [d]
+    // average of a/||a|| over the general rows: 2^-40 fixed point in 64-bit integers, so that the shared
+    // accumulator is exact (hence reproducible) under any interleaving of the warps
+    unsigned long long* avg_fx = (unsigned long long*)(smem + (size_t)NW * S * rowbuf);   // [d]
+    int* sing = (int*)(avg_fx + d);                                          // [d]
     int2* rowinfo = (int2*)align_up((size_t)(sing + d), 8);                 // [m_max] (cnt, off); cnt = 0: not general
     uint64_t* full = (uint64_t*)(rowinfo + p.m_max);                        // [NW*S]
     int* s_cnt = (int*)(full + NW * S);                                     // [16]
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(NT) scan_rows_kernel(ScanParams p) {
     const int m_b = p.m_rows ? min(max(p.m_rows[b], 0), p.m_max) : p.m_max;
     const float* A_b = p.A + (size_t)b * p.m_max * d;
 
-    for (int k = tid; k < NW * d; k += NT) avg_w[k] = 0.f;
+    for (int k = tid; k < d; k += NT) avg_fx[k] = 0ull;
     for (int k = tid; k < d; k += NT) sing[k] = 0;
     for (int k = tid; k < (int)(p.dpad / 4); k += NT) ctype_w[k] = 0u;
     for (int k = tid; k < p.m_max; k += NT) rowinfo[k] = make_int2(0, 0);
@@ -348,7 +350,6 @@ __global__ void __launch_bounds__(NT) scan_rows_kernel(ScanParams p) {
 
     int w_nvalid = 0, w_navg = 0, w_gennnz = 0, w_ngen = 0;
     float w_l1max = 0.f, w_l2max = 0.f;
-    float* myavg = avg_w + (size_t)warp * d;
     uint16_t* col_out = p.csr_col + (size_t)b * p.cap_nnz;
     float* val_out = p.csr_val + (size_t)b * p.cap_nnz;
     ulonglong2* hash_out = p.ghash + (size_t)b * p.m_max;       // row-indexed
@@ -372,26 +373,25 @@ __global__ void __launch_bounds__(NT) scan_rows_kernel(ScanParams p) {
                 if (kt >= (q0 << 2) && kt < e1) { float v = base[kt]; if (v != 0.f) acc.add(v, kt - e0); }
             }
             const float4* b4 = (const float4*)base;
-            for (int q = q0 + lane; q < q1 + lane; q += 64) {       // two independent words per trip
-                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-                if (q < q1) v0 = b4[q];
-                if (q + 32 < q1) v1 = b4[q + 32];
-                const uint32_t any0 = (__float_as_uint(v0.x) | __float_as_uint(v0.y) | __float_as_uint(v0.z) | __float_as_uint(v0.w)) << 1;
-                const uint32_t any1 = (__float_as_uint(v1.x) | __float_as_uint(v1.y) | __float_as_uint(v1.z) | __float_as_uint(v1.w)) << 1;
-                if (__ballot_sync(0xffffffffu, (any0 | any1) != 0u) == 0u) continue;
-                if (any0 != 0u) {
-                    const int k = (q << 2) - e0;
-                    if (v0.x != 0.f) acc.add(v0.x, k);
-                    if (v0.y != 0.f) acc.add(v0.y, k + 1);
-                    if (v0.z != 0.f) acc.add(v0.z, k + 2);
-                    if (v0.w != 0.f) acc.add(v0.w, k + 3);
+            for (int q = q0 + lane; q < q1 + lane; q += 128) {      // four independent 128-bit words per trip
+                float4 v[4];
+                uint32_t any[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (q + 32 * u < q1) v[u] = b4[q + 32 * u];
+                    any[u] = (__float_as_uint(v[u].x) | __float_as_uint(v[u].y) | __float_as_uint(v[u].z) | __float_as_uint(v[u].w)) << 1;
                 }
-                if (any1 != 0u) {
-                    const int k = ((q + 32) << 2) - e0;
-                    if (v1.x != 0.f) acc.add(v1.x, k);
-                    if (v1.y != 0.f) acc.add(v1.y, k + 1);
-                    if (v1.z != 0.f) acc.add(v1.z, k + 2);
-                    if (v1.w != 0.f) acc.add(v1.w, k + 3);
+                if (__ballot_sync(0xffffffffu, (any[0] | any[1] | any[2] | any[3]) != 0u) == 0u) continue;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (any[u] != 0u) {
+                        const int k = ((q + 32 * u) << 2) - e0;
+                        if (v[u].x != 0.f) acc.add(v[u].x, k);
+                        if (v[u].y != 0.f) acc.add(v[u].y, k + 1);
+                        if (v[u].z != 0.f) acc.add(v[u].z, k + 2);
+                        if (v[u].w != 0.f) acc.add(v[u].w, k + 3);
+                    }
                 }
             }
         } else {
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(NT) scan_rows_kernel(ScanParams p) {
                 const float v = k < d ? row[k] : 0.f;
                 const unsigned nzm = __ballot_sync(0xffffffffu, v != 0.f);
                 if (v != 0.f) {
-                    if (av) myavg[k] = fmaf(v, inv, myavg[k]);
+                    if (av) atomicAdd(&avg_fx[k], (unsigned long long)__double2ll_rn((double)v * (double)inv * 1099511627776.0));
                     if (fits) {
                         const int pos = w + __popc(nzm & ((1u << lane) - 1u));
                         col_out[pos] = (uint16_t)k; val_out[pos] = v;
@@ -519,11 +519,7 @@ __global__ void __launch_bounds__(NT) scan_rows_kernel(ScanParams p) {
     float* avg_out = p.avg + (size_t)b * p.dpad;
     for (int k = tid; k < (int)p.dpad; k += NT) {
         float acc = 0.f;
-        if (k < d) {
-#pragma unroll
-            for (int w2 = 0; w2 < NW; ++w2) acc += avg_w[(size_t)w2 * d + k];
-            acc = (acc + (float)sing[k]) * ninv;
-        }
+        if (k < d) acc = ((float)((double)(long long)avg_fx[k] * (1.0 / 1099511627776.0)) + (float)sing[k]) * ninv;
         avg_out[k] = acc;
     }
     uint32_t* ct_out = (uint32_t*)(p.ctype + (size_t)b * p.dpad);
@@ -540,7 +536,7 @@ __global__ void __launch_bounds__(NT) scan_rows_kernel(ScanParams p) {
 size_t scan_rows_smem_bytes(int d, int m_max, int NW, int S, size_t* rowbuf_out) {
     const size_t rowbuf = align_up((size_t)d * 4 + 32, 128);
     const int64_t dpad = (int64_t)align_up((size_t)d, 16);
-    size_t o = (size_t)NW * S * rowbuf + (size_t)NW * d * 4 + (size_t)d * 4 + 8;
+    size_t o = (size_t)NW * S * rowbuf + (size_t)d * 8 + (size_t)d * 4 + 8;
     o += (size_t)m_max * 8 + (size_t)NW * S * 8 + 16 * 4 + 2 * NW * 4 + 16 + (size_t)dpad;
     if (rowbuf_out) *rowbuf_out = rowbuf;
     return align_up(o, 16);
@@ -562,19 +558,26 @@ size_t scan_smem_bytes(int d, int R, int stages, size_t* stage_stride_out) {
 cudaError_t launch_scan(const ScanParams& p0, cudaStream_t stream) {
     ScanParams p = p0;
     constexpr int NT = 256;
-    {   // warp-streaming kernel whenever eight 3-deep row rings fit in shared memory
-        size_t rowbuf = 0;
-        const size_t smem = scan_rows_smem_bytes(p.d, p.m_max, NT / 32, 3, &rowbuf);
+    {   // warp-streaming kernel whenever eight row rings fit in shared memory: depth 2 with two CTAs
+        // per SM if that fits (more independent row streams), else depth 3 with one CTA per SM
         const char* force = getenv("CAVE_SCAN_KERNEL");
+        const char* sdepth = getenv("CAVE_SCAN_STAGES");
+        size_t rowbuf = 0;
+        int S = 2;
+        size_t smem = scan_rows_smem_bytes(p.d, p.m_max, NT / 32, 2, &rowbuf);
+        if (smem > 113 * 1024 || (sdepth && sdepth[0] == '3')) { S = 3; smem = scan_rows_smem_bytes(p.d, p.m_max, NT / 32, 3, &rowbuf); }
         if (smem <= 220 * 1024 && !(force && force[0] == 't')) {
-            p.stage_stride = rowbuf; p.R = 1; p.stages = 3;
-            static size_t configured_rows = 0;
-            if (smem > configured_rows) {
-                cudaError_t e = cudaFuncSetAttribute(scan_rows_kernel<NT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            p.stage_stride = rowbuf; p.R = 1; p.stages = S;
+            static size_t configured2 = 0, configured3 = 0;
+            size_t& conf = S == 2 ? configured2 : configured3;
+            if (smem > conf) {
+                cudaError_t e = S == 2 ? cudaFuncSetAttribute(scan_rows_kernel<NT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                       : cudaFuncSetAttribute(scan_rows_kernel<NT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
-                configured_rows = smem;
+                conf = smem;
             }
-            scan_rows_kernel<NT, 3><<<dim3((unsigned)p.B), dim3(NT), smem, stream>>>(p);
+            if (S == 2) scan_rows_kernel<NT, 2><<<dim3((unsigned)p.B), dim3(NT), smem, stream>>>(p);
+            else scan_rows_kernel<NT, 3><<<dim3((unsigned)p.B), dim3(NT), smem, stream>>>(p);
             return cudaGetLastError();
         }
     }

@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(NT) scan_kernel(ScanParams p) {
                             if (v != 0.f) {
                                 const int pos = w + __popc(nzm & ((1u << lane) - 1u));
                                 col_out[pos] = (uint16_t)k; val_out[pos] = v;
+                                if (!(v == (float)(int)v && fabsf(v) <= 127.f)) s_cnt[7] = 1;
                                 const uint32_t bits = __float_as_uint(v);
                                 hp += mix64d(((uint64_t)k << 32) | bits);
                                 hn += mix64d(((uint64_t)k << 32) | (bits ^ 0x80000000u));
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(NT) scan_kernel(ScanParams p) {
     for (int k = tid; k < (int)(p.dpad / 4); k += NT) ct_out[k] = ((const uint32_t*)ctype)[k];
     if (tid == 0) {
         p.nvalid[b] = s_cnt[0]; p.navg[b] = s_cnt[1]; p.ngen[b] = t_ngen; p.gennnz[b] = t_gennnz; p.nsingc[b] = s_cnt[4];
-        p.csr_ok[b] = overflow ? 0 : 1;
+        p.csr_ok[b] = overflow ? 0 : (s_cnt[7] ? 1 : 3);
         p.maxl1[b] = t_l1max; p.maxl2[b] = t_l2max;
     }
 }
@@ -451,6 +452,7 @@ __global__ void __launch_bounds__(NT) scan_rows_kernel(ScanParams p) {
                     if (fits) {
                         const int pos = w + __popc(nzm & ((1u << lane) - 1u));
                         col_out[pos] = (uint16_t)k; val_out[pos] = v;
+                        if (!(v == (float)(int)v && fabsf(v) <= 127.f)) s_cnt[7] = 1;      // not an int8 value
                         const uint32_t bits = __float_as_uint(v);
                         hp += mix64d(((uint64_t)k << 32) | bits);
                         hn += mix64d(((uint64_t)k << 32) | (bits ^ 0x80000000u));
@@ -528,7 +530,7 @@ __global__ void __launch_bounds__(NT) scan_rows_kernel(ScanParams p) {
         float m1 = 0.f, m2 = 0.f;
         for (int w2 = 0; w2 < NW; ++w2) { m1 = fmaxf(m1, s_max[w2]); m2 = fmaxf(m2, s_max[NW + w2]); }
         p.nvalid[b] = s_cnt[0]; p.navg[b] = s_cnt[1]; p.ngen[b] = s_cnt[2]; p.gennnz[b] = s_cnt[3]; p.nsingc[b] = s_cnt[4];
-        p.csr_ok[b] = s_cnt[6] ? 0 : 1;
+        p.csr_ok[b] = s_cnt[6] ? 0 : (s_cnt[7] ? 1 : 3);       // bit 1: every packed value is an int8
         p.maxl1[b] = m1; p.maxl2[b] = m2;
     }
 }

@@ -265,7 +265,7 @@ struct Instance {
     const uint8_t* ctype;   // [d] singleton cone type per coordinate            (from the pack)
     const float* avg;       // [d] average unit normal (src/cave.py:222-228)     (from the pack)
     int d, ngen, gen_nnz, nvalid, nsingc;
-    // packed CSR of the general rows written by the scan kernel (valid iff csr_ok)
+    // packed CSR of the general rows written by the scan kernel (valid iff csr_ok & 1; bit 1: all int8)
     int csr_ok;
     const hash_t* ghash;    // indexed by row: hash(row), hash(-row)   (general rows only)
     const uint16_t* pcol;
@@ -286,12 +286,13 @@ struct NewtonWork {
     int d, mB, nv;
     HPtr<T, HOT> c, r, rt;
     HPtr<uint8_t, HOT> ctype;
-    int* rptr; uint16_t* rcol; float* rval;      // CSR of the general rows
+    int* rptr; uint16_t* rcol; void* rval;       // CSR of the general rows (values float, or int8 if i8)
+    bool i8;
     int* grow;                                    // general row -> row index in A
     uint8_t* rtype;                               // 0 bounded, 1 free (merged +-), 2 dropped
     int* vrow;                                    // variable -> CSR row
     HPtr<uint8_t, HOT> vfree;                     // variable is sign-free
-    int* cptr; uint16_t* crow; float* cval;      // CSC over variables
+    int* cptr; uint16_t* crow; void* cval;       // CSC over variables
     HPtr<T, HOT> nu, g, dir, nut;
     HPtr<int, HOT> flist;                         // free-set variable ids
     HPtr<int, HOT> fpos;                          // variable -> position in flist or -1
@@ -302,12 +303,13 @@ struct NewtonWork {
     HPtr<TH, HOT> xs;                             // [nv] Newton step on the free set, then 1/d_j
 };
 
-template <class T, class TH, bool HOT>
-CAVE_DEV void nw_eval2(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> nu, HPtr<T, HOT> rout, T& f, T& extra) {
+template <class VT, class T, class TH, bool HOT>
+CAVE_DEV void nw_eval2_t(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> nu, HPtr<T, HOT> rout, T& f, T& extra) {
+    const VT* cval = (const VT*)W.cval;
     T acc = (T)0;
     for (int k = cx.tid; k < W.d; k += cx.nthr) {
         T rk = W.c[k];
-        for (int e = W.cptr[k]; e < W.cptr[k + 1]; ++e) rk -= (T)W.cval[e] * (T)nu[W.crow[e]];
+        for (int e = W.cptr[k]; e < W.cptr[k + 1]; ++e) rk -= (T)cval[e] * (T)nu[W.crow[e]];
         rout[k] = rk;
         T q = psi(rk, (int)(uint8_t)W.ctype[k]);
         acc += q * q;
@@ -315,27 +317,37 @@ CAVE_DEV void nw_eval2(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> nu
     cx.block_sum2(acc, extra);
     f = (T)0.5 * acc;
 }
-
 template <class T, class TH, bool HOT>
-CAVE_DEV void nw_grad(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> r, HPtr<T, HOT> g) {
+CAVE_DEV void nw_eval2(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> nu, HPtr<T, HOT> rout, T& f, T& extra) {
+    if (W.i8) nw_eval2_t<int8_t>(cx, W, nu, rout, f, extra); else nw_eval2_t<float>(cx, W, nu, rout, f, extra);
+}
+
+template <class VT, class T, class TH, bool HOT>
+CAVE_DEV void nw_grad_t(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> r, HPtr<T, HOT> g) {
+    const VT* rval = (const VT*)W.rval;
     for (int v = cx.warp; v < W.nv; v += cx.nwarp) {
         int row = W.vrow[v];
         T acc = (T)0;
         for (int e = W.rptr[row] + cx.lane; e < W.rptr[row + 1]; e += Ctx::WS) {
             int k = W.rcol[e];
-            acc += (T)W.rval[e] * psi((T)r[k], (int)(uint8_t)W.ctype[k]);
+            acc += (T)rval[e] * psi((T)r[k], (int)(uint8_t)W.ctype[k]);
         }
         acc = cx.warp_sum(acc);
         if (cx.lane == 0) g[v] = -acc;
     }
     cx.sync();
 }
+template <class T, class TH, bool HOT>
+CAVE_DEV void nw_grad(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> r, HPtr<T, HOT> g) {
+    if (W.i8) nw_grad_t<int8_t>(cx, W, r, g); else nw_grad_t<float>(cx, W, r, g);
+}
 
 // Fold the columns whose activity psi'(r_k) changed since the last call into H = B W B^T
 // (lower triangle over ALL variables): H += +-b_k b_k^T with shared-memory atomics.  After the
 // first iterations only a handful of coordinates change sign, so this is almost free.
-template <class T, class TH, bool HOT>
-CAVE_DEV void nw_hessian_update(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> r) {
+template <class VT, class T, class TH, bool HOT>
+CAVE_DEV void nw_hessian_update_t(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> r) {
+    const VT* cval = (const VT*)W.cval;
     const int nv = W.nv;
     for (int k = cx.tid; k < W.d; k += cx.nthr) {
         const uint8_t now = psi_active((T)r[k], (int)(uint8_t)W.ctype[k]) ? 1 : 0;
@@ -345,15 +357,19 @@ CAVE_DEV void nw_hessian_update(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T
         const int s = W.cptr[k], e = W.cptr[k + 1];
         for (int e1 = s; e1 < e; ++e1) {
             const int a = W.crow[e1];
-            const TH va = sg * (TH)W.cval[e1];
+            const TH va = sg * (TH)cval[e1];
             for (int e2 = s; e2 <= e1; ++e2) {
                 const int b = W.crow[e2];
                 const int hi = a > b ? a : b, lo = a > b ? b : a;
-                W.H.atomic_add((size_t)hi * nv + lo, va * (TH)W.cval[e2]);
+                W.H.atomic_add((size_t)hi * nv + lo, va * (TH)cval[e2]);
             }
         }
     }
     cx.sync();
+}
+template <class T, class TH, bool HOT>
+CAVE_DEV void nw_hessian_update(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> r) {
+    if (W.i8) nw_hessian_update_t<int8_t>(cx, W, r); else nw_hessian_update_t<float>(cx, W, r);
 }
 
 // Inclusive scan of x[0..n) in place by warp 0 (callers synchronise before and after).
@@ -422,7 +438,8 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
         // fallback: build the CSR of ALL general rows from A (one warp per row, ballot compaction keeps
         // the columns sorted), computing the hashes and norms the scan kernel could not deliver
         W.rcol = ar.get<uint16_t>(in.gen_nnz + 8);
-        W.rval = ar.get<float>(in.gen_nnz + 4);
+        float* rvalf = ar.get<float>(in.gen_nnz + 4);
+        W.rval = rvalf;
         if (ar.overflow) return false;
         T l1max = (T)0, l2max = (T)0;
         for (int i = cx.warp; i < mB; i += cx.nwarp) {
@@ -444,7 +461,7 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
                     unsigned m = cx.ballot(nz);
                     if (nz) {
                         int p = off + cx.lanes_below(m);
-                        W.rcol[p] = (uint16_t)k; W.rval[p] = v[u];
+                        W.rcol[p] = (uint16_t)k; rvalf[p] = v[u];
                         union { float f; uint32_t u; } cv; cv.f = v[u];
                         hp += mix64(((uint64_t)k << 32) | cv.u);
                         hn += mix64(((uint64_t)k << 32) | (cv.u ^ 0x80000000u));
@@ -462,7 +479,7 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
         }
         cx.block_max2(l1max, l2max);    // (barriers inside make the CSR visible)
         *maxrow_l1 = l1max; *maxrow_l2sq = l2max;
-        mcol = W.rcol; mval = W.rval;
+        mcol = W.rcol; mval = rvalf;
     } else {
         *maxrow_l1 = (T)in.maxl1; *maxrow_l2sq = (T)in.maxl2;
     }
@@ -527,12 +544,15 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     const int nv = W.nv;
     W.H = ar.geth<HOT, TH>((size_t)nv * nv + 1);
     W.L = ar.geth<HOT, TH>((size_t)(nv + 1) * ((nv + 1) | 1) + 1);
+    // the CSC feeds eval (several times per iteration) and the Hessian update, the CSR only the gradient:
+    // the CSC gets shared memory first.  Integer-valued rows (every shipped model) are kept as int8.
+    W.i8 = (in.csr_ok & 3) == 3;
+    W.crow = ar.get<uint16_t>(nnzc + 1);
+    if (W.i8) W.cval = ar.get<int8_t>(nnzc + 1); else W.cval = ar.get<float>(nnzc + 1);
     if (in.csr_ok) {
         W.rcol = ar.get<uint16_t>(nnzc + 8);
-        W.rval = ar.get<float>(nnzc + 4);
+        if (W.i8) W.rval = ar.get<int8_t>(nnzc + 4); else W.rval = ar.get<float>(nnzc + 4);
     }
-    W.crow = ar.get<uint16_t>(nnzc + 1);
-    W.cval = ar.get<float>(nnzc + 1);
     if (ar.overflow) return false;
     if (in.csr_ok) {
         // rptr over variables, then one warp per kept row copies its non-zeros from the pack
@@ -543,7 +563,8 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
         cx.sync();
         for (int v = cx.warp; v < nv; v += cx.nwarp) {
             const int src = goff[W.vrow[v]], dst = W.rptr[v], n = W.rptr[v + 1] - dst;
-            for (int e = cx.lane; e < n; e += Ctx::WS) { W.rcol[dst + e] = in.pcol[src + e]; W.rval[dst + e] = in.pval[src + e]; }
+            if (W.i8) for (int e = cx.lane; e < n; e += Ctx::WS) { W.rcol[dst + e] = in.pcol[src + e]; ((int8_t*)W.rval)[dst + e] = (int8_t)in.pval[src + e]; }
+            else for (int e = cx.lane; e < n; e += Ctx::WS) { W.rcol[dst + e] = in.pcol[src + e]; ((float*)W.rval)[dst + e] = in.pval[src + e]; }
         }
         cx.sync();
         for (int v = cx.tid; v < nv; v += cx.nthr) W.vrow[v] = v;
@@ -569,7 +590,8 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
         int row = W.vrow[v];
         for (int e = W.rptr[row] + cx.lane; e < W.rptr[row + 1]; e += Ctx::WS) {
             int p = cx.atomic_add(&W.cur[W.rcol[e]], 1);
-            W.crow[p] = (uint16_t)v; W.cval[p] = W.rval[e];
+            W.crow[p] = (uint16_t)v;
+            if (W.i8) ((int8_t*)W.cval)[p] = ((const int8_t*)W.rval)[e]; else ((float*)W.cval)[p] = ((const float*)W.rval)[e];
         }
     }
     cx.sync();
@@ -577,9 +599,16 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
         int s = W.cptr[k], e = W.cptr[k + 1];
         if (e - s <= 64)
             for (int a = s + 1; a < e; ++a) {
-                uint16_t rr = W.crow[a]; float vv = W.cval[a]; int b = a - 1;
-                while (b >= s && W.crow[b] > rr) { W.crow[b + 1] = W.crow[b]; W.cval[b + 1] = W.cval[b]; --b; }
-                W.crow[b + 1] = rr; W.cval[b + 1] = vv;
+                uint16_t rr = W.crow[a]; int b = a - 1;
+                if (W.i8) {
+                    int8_t* cv = (int8_t*)W.cval; int8_t vv = cv[a];
+                    while (b >= s && W.crow[b] > rr) { W.crow[b + 1] = W.crow[b]; cv[b + 1] = cv[b]; --b; }
+                    W.crow[b + 1] = rr; cv[b + 1] = vv;
+                } else {
+                    float* cv = (float*)W.cval; float vv = cv[a];
+                    while (b >= s && W.crow[b] > rr) { W.crow[b + 1] = W.crow[b]; cv[b + 1] = cv[b]; --b; }
+                    W.crow[b + 1] = rr; cv[b + 1] = vv;
+                }
             }
     }
     cx.sync();

@@ -58,7 +58,8 @@ static void run(const float* A, int B, int m, int d, const double* pred, double 
         HostPack pk; host_pack(A + (size_t)b * m * d, m, d, pk);
         Instance in; in.A = A + (size_t)b * m * d; in.gen = pk.gen.data(); in.ctype = pk.ctype.data(); in.avg = pk.avg.data();
         in.d = d; in.ngen = (int)pk.gen.size(); in.gen_nnz = pk.gen_nnz; in.nvalid = pk.nvalid; in.nsingc = pk.nsingc;
-        in.csr_ok = (force_path & 2) ? 0 : 1;                                  // bit 1: rebuild the CSR from A
+        bool all8 = true; for (float v : pk.val) all8 = all8 && v == (float)(int)v && fabsf(v) <= 127.f;
+        in.csr_ok = (force_path & 2) ? 0 : (all8 ? 3 : 1);                                  // bit 1: rebuild the CSR from A
         in.ghash = pk.ghash.data(); in.pcol = pk.col.data(); in.pval = pk.val.data(); in.maxl1 = pk.maxl1; in.maxl2 = pk.maxl2;
         if (force_path & 1) in.nsingc = 0 == in.nsingc ? 1 : in.nsingc;       // bit 0: force the Newton path
         Ctx cx; EpiParams ep; ep.mode = mode; ep.inner_ratio = inner_ratio; ep.sign = sign; ep.gscale = gscale;

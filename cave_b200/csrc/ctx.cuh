@@ -205,10 +205,10 @@ template <class U> struct HPtr<U, true> {
     uint32_t a;
     __device__ __forceinline__ HPtr() : a(0) {}
     __device__ __forceinline__ explicit HPtr(U* q) : a((uint32_t)__cvta_generic_to_shared(q)) {}
-    __device__ __forceinline__ SRef<U> operator[](size_t i) const { SRef<U> r; r.a = a + (uint32_t)i * (uint32_t)sizeof(U); return r; }
-    __device__ __forceinline__ HPtr operator+(size_t o) const { HPtr h; h.a = a + (uint32_t)o * (uint32_t)sizeof(U); return h; }
+    __device__ __forceinline__ SRef<U> operator[](uint32_t i) const { SRef<U> r; r.a = a + i * (uint32_t)sizeof(U); return r; }
+    __device__ __forceinline__ HPtr operator+(uint32_t o) const { HPtr h; h.a = a + o * (uint32_t)sizeof(U); return h; }
     __device__ __forceinline__ U* raw() const { return (U*)__cvta_shared_to_generic((size_t)a); }
-    __device__ __forceinline__ void atomic_add(size_t i, U v) const { SmemOps<U>::add(a + (uint32_t)i * (uint32_t)sizeof(U), v); }
+    __device__ __forceinline__ void atomic_add(uint32_t i, U v) const { SmemOps<U>::add(a + i * (uint32_t)sizeof(U), v); }
 };
 template <class U> struct HPtr<U, false> {
     U* p;

@@ -79,13 +79,23 @@ struct Arena {
     }
 };
 
-template <class T> CAVE_DEV T psi(T r, int t) {
-    return t == 0 ? r : (t == 1 ? (r < (T)0 ? r : (T)0) : (t == 2 ? (r > (T)0 ? r : (T)0) : (T)0));
-}
+// ctype bit0: a row +a*e_k exists (positive residual absorbed); bit1: a row -a*e_k exists (negative absorbed)
 template <class T> CAVE_DEV bool psi_active(T r, int t) {
-    return t == 0 ? true : (t == 1 ? r < (T)0 : (t == 2 ? r > (T)0 : false));
+    return t == 0 ? true : (r > (T)0 ? !(t & 1) : (r < (T)0 ? !(t & 2) : false));
 }
+template <class T> CAVE_DEV T psi(T r, int t) { return psi_active(r, t) ? r : (T)0; }
 template <class T> CAVE_DEV T cabs(T v) { return v < (T)0 ? -v : v; }
+// reciprocal of a positive pivot without a full-precision division on the critical path
+CAVE_DEV float fast_rcp(float x) { return 1.0f / x; }
+CAVE_DEV double fast_rcp(double x) {
+#ifdef CAVE_HOST_SIM
+    return 1.0 / x;
+#else
+    double y = (double)__frcp_rn((float)x);      // 24 bits
+    y = y * (2.0 - x * y);                        // 48 bits
+    return y * (2.0 - x * y);                     // full
+#endif
+}
 template <class T> CAVE_DEV T eps_mach();
 template <> CAVE_DEV double eps_mach<double>() { return 2.220446049250313e-16; }
 template <> CAVE_DEV float eps_mach<float>() { return 1.1920929e-7f; }
@@ -189,7 +199,7 @@ CAVE_DEV void ldlt_blocked(Ctx& cx, PL L, int nf, int ldl, PL invd, TH piv_floor
                 for (int jj = 0; jj < PB; ++jj) {
                     if (jj < pw) {
                         TH dj = __shfl_sync(0xffffffffu, a[0][jj], jj);
-                        const TH inv = (TH)1 / (dj > piv_floor ? dj : piv_floor);
+                        const TH inv = fast_rcp(dj > piv_floor ? dj : piv_floor);
                         if (cx.lane == 0) invd[j0 + jj] = inv;
                         TH pc[PB];
 #pragma unroll
@@ -624,7 +634,7 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<T, HOT> 
     if (!nw_setup<T, TH, HOT>(cx, in, ar, W, &l1max, &l2max)) { out.status = ST_NOSPACE; out.iters = 0; out.r = r.raw(); return; }
     const int nv = W.nv;
     const T scale = (l1max > (T)1 ? l1max : (T)1) * (cnorm > (T)1e-30 ? cnorm : (T)1e-30);
-    const T tol = (T)(opt.tol > 0 ? opt.tol : 1e-12) * scale;
+    const T tol = (T)(opt.tol > 0 ? opt.tol : 1e-12) * scale;   // tight: the rnorm < 1e-7 inside-the-cone test depends on it
     const int max_iter = opt.max_iter > 0 ? opt.max_iter : 200;
     const int max_ls = opt.max_ls > 0 ? opt.max_ls : 40;
     // Tikhonov term: relative to the largest possible diagonal entry of B W B^T (max_i ||b_i||^2)

@@ -241,3 +241,30 @@ def test_long_rows_use_tile_kernel_and_fallback_csr():
     out = _run(c, A2, mode=1)
     _check(out, ref, 1e-5, 1)
     assert not (out["status"] & 0x100).any()                       # Newton path, CSR rebuilt from A
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_reproducible_at_scale_and_against_kernel_source_on_cpu(precision):
+    """Race detector: 592 TSP-50 instances (two full waves of resident CTAs) three times, bitwise equal;
+    and the first instances against the same kernel source compiled for the CPU (tests/hostsim)."""
+    import sys
+    from cave_b200 import cave_forward_backward, synth
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+    import sim
+    dev = _cuda()
+    insts = synth.make_batch("tsp50", 592, seed=21)
+    A = synth.densify(insts, device=dev)
+    pred_np = synth.predictions(insts, 21, "near")
+    pred = torch.tensor(pred_np, dtype=torch.float64, device=dev)
+    runs = []
+    for _ in range(3):
+        o = cave_forward_backward(pred, A, -1.0, 1, 0.2, "none", precision=precision, want_proj=True, want_status=True)
+        runs.append({k: v.clone() for k, v in o.items()})
+    for k in ("loss", "grad", "proj", "rnorm", "iters"):
+        assert torch.equal(runs[0][k], runs[1][k]) and torch.equal(runs[0][k], runs[2][k]), k
+    assert int((runs[0]["status"] & 0xff).max()) == 0
+    n = 6
+    ref = sim.forward_backward(pred_np[:n], A[:n].cpu().numpy(), mode=1, inner_ratio=0.2, reduction="none",
+                               compute_f32=precision == "fp32")
+    np.testing.assert_allclose(runs[0]["proj"][:n].cpu().numpy(), ref["proj"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_array_equal(runs[0]["iters"][:n].cpu().numpy(), ref["iters"])

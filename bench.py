@@ -256,6 +256,7 @@ def run_ours(args):
 
     # ---- end to end through the module call with host tensors
     e2e = None
+    e2e_resident = None
     if not args.no_e2e:
         class Model:
             modelSense = EPO.MINIMIZE
@@ -289,6 +290,33 @@ def run_ours(args):
         e2e = {"value": B * world / dt, "unit": UNIT, "h2d_bytes_per_step": int(A_host.numel() * 4 + pred_host.numel() * 4),
                "d2h_bytes_per_step": int(pred_host.numel() * 4 + 4), "ms_per_step": dt * 1e3, "steps": n_e2e,
                "note": "module call with pinned host pred_cost and tight_ctrs; PCIe copy of the dense constraints dominates"}
+        # the same module call with the constraints kept resident on the device (CavePack over the dataset +
+        # per-step instance index): what a multi-epoch trainer does, since A_i never changes between epochs
+        perm_host = torch.randperm(B, dtype=torch.int32).pin_memory()
+
+        def e2e_resident_step():
+            p = pred_host.requires_grad_(True)
+            p.grad = None
+            loss = mod(p, pack, index=perm_host)       # H2D: pred_cost + index; D2H: loss + gradient
+            loss.backward()
+            return float(loss)
+
+        e2e_resident_step()
+        n_res = max(3, args.steps)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_res):
+            e2e_resident_step()
+        barrier()
+        dtr = (time.perf_counter() - t0) / n_res
+        if world > 1:
+            t = torch.tensor([dtr], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtr = float(t.item())
+        e2e_resident = {"value": B * world / dtr, "unit": UNIT, "h2d_bytes_per_step": int(pred_host.numel() * 4 + B * 4),
+                        "d2h_bytes_per_step": int(pred_host.numel() * 4 + 4), "ms_per_step": dtr * 1e3, "steps": n_res,
+                        "note": "device-resident packed dataset (pack built once, outside the timed region) + instance "
+                                "index per step; host pred_cost in, host loss and gradient out"}
         del A_host
 
     line = {
@@ -298,7 +326,7 @@ def run_ours(args):
         "config": {"workload": f"{args.workload} DFJ synthetic (SURVEY App. B), CaVE+ inner_ratio {ratio}, batch {B}/GPU, "
                                f"pred regime {args.regime}, dense float32 [B,{m_max},{d}] resident in HBM, cold pack",
                    "batch_per_gpu": B, "m_max": m_max, "d": d, "l2_policy": "inputs larger than L2 (A = %.1f GB)" % (scan_bytes / 1e9)},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * args.steps,
+        "clocks": clocks, "e2e": e2e, "e2e_resident_dataset": e2e_resident, "gpu_launches": 3 * args.steps,
         "roofline": roofline, "kernels": kernels,
         "solver": {"status_counts": {str(k): int(v) for k, v in zip(*np.unique(status, return_counts=True))},
                    "iters_mean": float(iters.mean()), "iters_max": int(iters.max()), "loss": loss_val},

@@ -21,7 +21,7 @@ EXPORTS = ("cave_abi_version", "cave_last_error", "cave_get_limits", "cave_pack_
 class SolverOpts(ctypes.Structure):
     _fields_ = [("max_iter", ctypes.c_int32), ("max_linesearch", ctypes.c_int32), ("tol", ctypes.c_double),
                 ("cap_rows", ctypes.c_int64), ("cap_nnz", ctypes.c_int64), ("warm_pack", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)]
+                ("reserved", ctypes.c_int32), ("inst_index", ctypes.c_void_p), ("n_packed", ctypes.c_int64)]
 
 
 class Limits(ctypes.Structure):

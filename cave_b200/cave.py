@@ -20,10 +20,10 @@ import torch
 
 from . import _lib
 from ._pyepo_compat import EPO, optModule
-from .qpsolver import cave_forward_backward, project_cuda
+from .qpsolver import CavePack, cave_forward_backward, project_cuda
 
 _REFERENCE_SOLVERS = ("apgd", "clarabel", "nnls")
-_KERNEL_KWARGS = ("precision", "max_iter", "max_linesearch", "tol", "cap_rows", "cap_nnz", "device", "pack", "m_rows")
+_KERNEL_KWARGS = ("precision", "max_iter", "max_linesearch", "tol", "cap_rows", "cap_nnz", "device", "pack", "m_rows", "index")
 
 
 class _CaveCudaFunction(torch.autograd.Function):
@@ -32,6 +32,9 @@ class _CaveCudaFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pred_cost, tight_ctrs, sign, mode, inner_ratio, reduction, kwargs):
+        if isinstance(tight_ctrs, CavePack):      # device-resident dataset: kwargs carries index=
+            kwargs = dict(kwargs, pack=tight_ctrs)
+            tight_ctrs = None
         out = cave_forward_backward(pred_cost, tight_ctrs, sign, mode, inner_ratio, reduction, **kwargs)
         grad, loss = out["grad"], out["loss"]
         if grad.device != pred_cost.device:       # host tensors in -> host tensors out
@@ -67,11 +70,17 @@ class abstractConeAlignedCosine(optModule):
     def _mode(self) -> int:
         raise NotImplementedError
 
-    def forward(self, pred_cost: torch.Tensor, tight_ctrs: torch.Tensor) -> torch.Tensor:
+    def forward(self, pred_cost: torch.Tensor, tight_ctrs, index: torch.Tensor | None = None) -> torch.Tensor:
+        """``tight_ctrs``: the reference's padded [B, m, d] tensor (src/cave.py:55-57) — or, as an extension,
+        a ``CavePack`` built once over the whole dataset together with ``index`` [B] (dataset instance of
+        every batch row), which keeps the constraints resident on the device across epochs."""
         sign = self._sign()
         mode = self._mode()
+        kw = self._kernel_kwargs()
+        if index is not None:
+            kw = dict(kw, index=index)
         return _CaveCudaFunction.apply(pred_cost, tight_ctrs, sign, mode, getattr(self, "inner_ratio", 0.0),
-                                       self.reduction, self._kernel_kwargs())
+                                       self.reduction, kw)
 
 
 class exactConeAlignedCosine(abstractConeAlignedCosine):

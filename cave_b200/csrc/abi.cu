@@ -127,7 +127,10 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
                           const cave_solver_opts* opts, void* loss, void* loss_i, void* grad, void* proj, void* rnorm,
                           int32_t* status, int32_t* iters, void* pack, size_t pack_bytes, void* scratch,
                           size_t scratch_bytes, void* stream) {
-    if (!A || !pred || !loss_i || !grad || !pack || !scratch) return fail(CAVE_EINVAL, "A, pred, loss_i, grad, pack, scratch must not be null");
+    const bool indexed = opts && opts->inst_index;
+    if ((!A && !indexed) || !pred || !loss_i || !grad || !pack || !scratch) return fail(CAVE_EINVAL, "A, pred, loss_i, grad, pack, scratch must not be null");
+    if (indexed && !opts->warm_pack) return fail(CAVE_EINVAL, "inst_index needs warm_pack (a pack built over the whole dataset)");
+    if (indexed && opts->n_packed <= 0) return fail(CAVE_EINVAL, "n_packed must be positive with inst_index");
     if (int e = check_shape(B, m_max, d)) return e;
     if (mode < CAVE_MODE_EXACT || mode > CAVE_MODE_HEURISTIC) return fail(CAVE_EINVAL, "bad mode %d", mode);
     if (reduction < CAVE_REDUCE_MEAN || reduction > CAVE_REDUCE_NONE) return fail(CAVE_EINVAL, "bad reduction %d", reduction);
@@ -138,7 +141,9 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     if (reduction != CAVE_REDUCE_NONE && !loss) return fail(CAVE_EINVAL, "loss must not be null for mean/sum");
     if (((uintptr_t)scratch & 255) != 0 || ((uintptr_t)pack & 255) != 0) return fail(CAVE_EINVAL, "pack and scratch must be 256-byte aligned");
 
-    const cave::PackLayout PL = cave::make_pack_layout(B, m_max, d);
+    const int64_t Bpack = indexed ? opts->n_packed : B;
+    if (int e = check_shape(Bpack, m_max, d)) return e;
+    const cave::PackLayout PL = cave::make_pack_layout(Bpack, m_max, d);
     if (pack_bytes < PL.total) return fail(CAVE_ENOSPC, "pack buffer has %zu bytes, %zu needed", pack_bytes, PL.total);
     int64_t cr, cz;
     resolve_caps(opts, m_max, d, &cr, &cz);
@@ -174,6 +179,7 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     sp.gscale = reduction == CAVE_REDUCE_MEAN ? 1.0 / (double)B : 1.0;
     sp.max_iter = opts ? opts->max_iter : 0; sp.max_ls = opts ? opts->max_linesearch : 0; sp.tol = opts ? opts->tol : 0.0;
     sp.profile = env_int("CAVE_PROFILE", 0);
+    sp.inst_index = indexed ? opts->inst_index : nullptr;
     int threads = env_int("CAVE_SOLVE_THREADS", 256);
     if (threads != 128 && threads != 256 && threads != 512) threads = 256;
     ce = cave::launch_solve(sp, compute_dtype == CAVE_F32, io_dtype == CAVE_F32, (int)n_ctas, threads, st);

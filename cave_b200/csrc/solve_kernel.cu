@@ -33,16 +33,17 @@ __global__ void __launch_bounds__(512, 1) solve_kernel(SolveParams p) {
         const int b = s_b;
         __syncthreads();
         if (b >= p.B) break;
+        const size_t q = p.inst_index ? (size_t)p.inst_index[b] : (size_t)b;     // instance of the pack / of A
         Instance in;
-        in.A = p.A + (size_t)b * p.m_max * p.d;
-        in.gen = p.gen + (size_t)b * p.m_max;
-        in.ctype = p.ctype + (size_t)b * p.dpad;
-        in.avg = p.avg + (size_t)b * p.dpad;
-        in.d = p.d; in.ngen = p.ngen[b]; in.gen_nnz = p.gennnz[b]; in.nvalid = p.nvalid[b]; in.nsingc = p.nsingc[b];
-        in.csr_ok = p.csr_ok[b]; in.maxl1 = p.maxl1[b]; in.maxl2 = p.maxl2[b];
-        in.ghash = p.ghash + (size_t)b * p.m_max;
-        in.pcol = p.csr_col + (size_t)b * p.cap_nnz;
-        in.pval = p.csr_val + (size_t)b * p.cap_nnz;
+        in.A = p.A ? p.A + q * p.m_max * p.d : nullptr;
+        in.gen = p.gen + q * p.m_max;
+        in.ctype = p.ctype + q * p.dpad;
+        in.avg = p.avg + q * p.dpad;
+        in.d = p.d; in.ngen = p.ngen[q]; in.gen_nnz = p.gennnz[q]; in.nvalid = p.nvalid[q]; in.nsingc = p.nsingc[q];
+        in.csr_ok = p.csr_ok[q]; in.maxl1 = p.maxl1[q]; in.maxl2 = p.maxl2[q];
+        in.ghash = p.ghash + q * p.m_max;
+        in.pcol = p.csr_col + q * p.cap_nnz;
+        in.pval = p.csr_val + q * p.cap_nnz;
         solve_instance<T, TIO>(cx, in, smem, (size_t)p.smem_bytes, slot, p.slot_bytes, pred + (size_t)b * p.d, ep, opt, grad + (size_t)b * p.d,
                                proj ? proj + (size_t)b * p.d : nullptr, p.loss64 + b, p.rnorm64 + b,
                                p.status + b, p.iters + b);

@@ -35,6 +35,7 @@ struct SolveParams {
     int max_iter, max_ls;
     double tol;
     int profile;           // accumulate per-phase cycle counters (debug)
+    const int* inst_index; // nullable: batch position -> instance of the (dataset-wide) pack and of A
 };
 
 struct FinalizeParams {

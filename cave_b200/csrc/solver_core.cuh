@@ -438,6 +438,7 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     cx.sync();
     const uint16_t* mcol = in.pcol;     // where the merge verification reads the rows from
     const float* mval = in.pval;
+    if (!in.csr_ok && !in.A) { ar.overflow = true; return false; }     // rows neither packed nor resident
     if (!in.csr_ok) {
         // offsets of the CSR built here = exclusive scan of the counts
         if (cx.tid == 0) goff[0] = 0;
@@ -769,7 +770,7 @@ CAVE_DEV void lh_solve(Ctx& cx, const Instance& in, Arena& ar, T* c, T* r, T cno
     TH* L = ar.get<TH>((size_t)kmax * kmax + 1);
     TH* Gp = ar.get<TH>((size_t)kmax * kmax + 1);
     out.r = r; out.iters = 0;
-    if (ar.overflow) { out.status = ST_NOSPACE | ST_PATH_LH; return; }
+    if (ar.overflow || !in.A) { out.status = ST_NOSPACE | ST_PATH_LH; return; }    // dense rows are read from A
 
     for (int i = cx.tid; i < mB; i += cx.nthr) { st[i] = 0; grow[i] = in.gen[i].x; }
     for (int k = cx.tid; k < d; k += cx.nthr) r[k] = c[k];

@@ -24,9 +24,11 @@ _PRECISIONS = {"fp64": _lib.F64, "float64": _lib.F64, "double": _lib.F64,
                "fp32": _lib.F32, "float32": _lib.F32, "single": _lib.F32}
 
 
-def _opts(max_iter=None, max_linesearch=None, tol=None, cap_rows=None, cap_nnz=None, warm=False) -> _lib.SolverOpts:
+def _opts(max_iter=None, max_linesearch=None, tol=None, cap_rows=None, cap_nnz=None, warm=False,
+          index=None, n_packed=0) -> _lib.SolverOpts:
     return _lib.SolverOpts(int(max_iter or 0), int(max_linesearch or 0), float(tol or 0.0),
-                           int(cap_rows or 0), int(cap_nnz or 0), int(bool(warm)), 0)
+                           int(cap_rows or 0), int(cap_nnz or 0), int(bool(warm)), 0,
+                           index.data_ptr() if index is not None else None, int(n_packed))
 
 
 def _device_of(t: torch.Tensor, device) -> torch.device:
@@ -54,15 +56,22 @@ def _ptr(t):
 
 @dataclass
 class CavePack:
-    """Device-resident packed description of one ``tight_ctrs`` tensor (row classes, singleton cone
-    types, average normal).  A_i is constant across epochs, so a dataset can pack
-    once and pass ``pack=`` to skip the streaming pass over A on later calls."""
+    """Device-resident packed description of a ``tight_ctrs`` tensor (row classes, singleton cone types,
+    average normal, packed CSR of the general rows).  A_i is constant across epochs:
+
+    * per batch: ``pack=pack_constraints(bctr)`` skips the streaming pass over A on later calls with the
+      same batch tensor;
+    * per dataset: pack ALL instances once (``pack_constraints(all_ctrs)``) and pass ``pack=..., index=idx``
+      with ``idx[b]`` = dataset instance of batch row ``b`` — the device-resident replacement of
+      DataLoader + ``collate_fn`` (src/dataset.py:133-144).  ``ctrs`` keeps the dense dataset tensor
+      resident for instances whose general rows did not fit the packed CSR (``keep_dense=False`` drops it)."""
     buf: torch.Tensor
     shape: tuple
     data_ptr: int
+    ctrs: torch.Tensor | None = None
 
 
-def pack_constraints(tight_ctrs: torch.Tensor, m_rows: torch.Tensor | None = None) -> CavePack:
+def pack_constraints(tight_ctrs: torch.Tensor, m_rows: torch.Tensor | None = None, keep_dense: bool = True) -> CavePack:
     lib = _lib.load()
     if not tight_ctrs.is_cuda:
         raise ValueError("pack_constraints expects a CUDA tensor")
@@ -76,12 +85,13 @@ def pack_constraints(tight_ctrs: torch.Tensor, m_rows: torch.Tensor | None = Non
     with torch.cuda.device(A.device):
         stream = torch.cuda.current_stream(A.device).cuda_stream
         _lib.check(lib.cave_pack(_ptr(A), _ptr(m_rows), B, m, d, _ptr(buf), nbytes.value, ctypes.c_void_p(stream)))
-    return CavePack(buf, (B, m, d), A.data_ptr())
+    return CavePack(buf, (B, m, d), A.data_ptr(), A if keep_dense else None)
 
 
 def cave_forward_backward(pred_cost: torch.Tensor, tight_ctrs: torch.Tensor, sign: float, mode: int,
                           inner_ratio: float = 0.2, reduction: str = "mean", precision: str = "fp64",
                           want_proj: bool = False, want_status: bool = False, pack: CavePack | None = None,
+                          index: torch.Tensor | None = None,
                           m_rows: torch.Tensor | None = None, device=None, max_iter=None, max_linesearch=None,
                           tol=None, cap_rows=None, cap_nnz=None) -> dict:
     """One call of the hot path through the C ABI.  Returns a dict with ``loss`` (scalar for
@@ -89,6 +99,10 @@ def cave_forward_backward(pred_cost: torch.Tensor, tight_ctrs: torch.Tensor, sig
     gradient of one), and optionally ``proj``, ``rnorm``, ``status``, ``iters`` — all on the
     compute device, in ``pred_cost``'s dtype."""
     lib = _lib.load()
+    if index is not None:
+        return _forward_backward_indexed(lib, pred_cost, tight_ctrs, sign, mode, inner_ratio, reduction, precision,
+                                         want_proj, want_status, pack, index, device, max_iter, max_linesearch, tol,
+                                         cap_rows, cap_nnz)
     if pred_cost.dim() != 2 or tight_ctrs.dim() != 3 or tight_ctrs.shape[0] != pred_cost.shape[0] \
             or tight_ctrs.shape[2] != pred_cost.shape[1]:
         raise ValueError(f"shape mismatch: pred_cost {tuple(pred_cost.shape)}, tight_ctrs {tuple(tight_ctrs.shape)}")
@@ -136,6 +150,53 @@ def cave_forward_backward(pred_cost: torch.Tensor, tight_ctrs: torch.Tensor, sig
             _lib.REDUCE[reduction], _lib.F64 if io_dtype == torch.float64 else _lib.F32, compute,
             ctypes.byref(opts), _ptr(loss), _ptr(loss_i), _ptr(grad), _ptr(proj), _ptr(rnorm), _ptr(status),
             _ptr(iters), _ptr(pack_buf), pack_buf.numel(), _ptr(scratch), scratch.numel(), ctypes.c_void_p(stream)))
+    out = dict(loss=loss_i if reduction == "none" else loss, loss_i=loss_i, grad=grad)
+    if want_proj:
+        out["proj"], out["rnorm"] = proj, rnorm
+    if want_status:
+        out["status"], out["iters"], out["rnorm"] = status, iters, rnorm
+    return out
+
+
+def _forward_backward_indexed(lib, pred_cost, ctrs, sign, mode, inner_ratio, reduction, precision, want_proj,
+                              want_status, pack, index, device, max_iter, max_linesearch, tol, cap_rows, cap_nnz) -> dict:
+    """Batch = rows ``index`` of a dataset whose constraints were packed once (device-resident dataset)."""
+    if pack is None:
+        raise ValueError("index= needs pack= (pack_constraints over the whole dataset)")
+    if reduction not in _lib.REDUCE:
+        raise ValueError(f"No reduction '{reduction}'.")
+    if precision not in _PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+    dev = pack.buf.device
+    N, m, d = pack.shape
+    if pred_cost.dim() != 2 or pred_cost.shape[1] != d or index.dim() != 1 or index.shape[0] != pred_cost.shape[0]:
+        raise ValueError(f"shape mismatch: pred_cost {tuple(pred_cost.shape)}, index {tuple(index.shape)}, pack {pack.shape}")
+    io_dtype = torch.float64 if pred_cost.dtype == torch.float64 else torch.float32
+    pred = _to_device(pred_cost.detach(), dev, io_dtype)
+    idx = _to_device(index.detach(), dev, torch.int32)
+    A = ctrs if ctrs is not None else pack.ctrs
+    if A is not None and (not A.is_cuda or A.device != dev or tuple(A.shape) != (N, m, d) or A.dtype != torch.float32):
+        raise ValueError("the dense dataset tensor must be the float32 CUDA tensor the pack was built from")
+    B = pred.shape[0]
+    compute = _PRECISIONS[precision]
+    opts = _opts(max_iter, max_linesearch, tol, cap_rows, cap_nnz, warm=True, index=idx, n_packed=N)
+    nb = ctypes.c_size_t()
+    _lib.check(lib.cave_scratch_bytes(B, m, d, compute, ctypes.byref(opts), ctypes.byref(nb)))
+    scratch = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+    loss = torch.empty((), dtype=io_dtype, device=dev)
+    loss_i = torch.empty(B, dtype=io_dtype, device=dev)
+    grad = torch.empty((B, d), dtype=io_dtype, device=dev)
+    proj = torch.empty((B, d), dtype=io_dtype, device=dev) if want_proj else None
+    rnorm = torch.empty(B, dtype=io_dtype, device=dev) if (want_proj or want_status) else None
+    status = torch.empty(B, dtype=torch.int32, device=dev) if want_status else None
+    iters = torch.empty(B, dtype=torch.int32, device=dev) if want_status else None
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.cave_forward_backward(
+            _ptr(A), None, _ptr(pred), B, m, d, float(sign), int(mode), float(inner_ratio),
+            _lib.REDUCE[reduction], _lib.F64 if io_dtype == torch.float64 else _lib.F32, compute,
+            ctypes.byref(opts), _ptr(loss), _ptr(loss_i), _ptr(grad), _ptr(proj), _ptr(rnorm), _ptr(status),
+            _ptr(iters), _ptr(pack.buf), pack.buf.numel(), _ptr(scratch), scratch.numel(), ctypes.c_void_p(stream)))
     out = dict(loss=loss_i if reduction == "none" else loss, loss_i=loss_i, grad=grad)
     if want_proj:
         out["proj"], out["rnorm"] = proj, rnorm

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CAVE_B200_ABI_VERSION 1
+#define CAVE_B200_ABI_VERSION 2
 
 /* error codes */
 #define CAVE_OK 0
@@ -68,12 +68,19 @@ typedef struct cave_solver_opts {
     int32_t max_iter;        /* Newton iterations / LH pivots cap; <= 0 -> default (200 / 3*m) */
     int32_t max_linesearch;  /* Armijo halvings cap; <= 0 -> default 40                        */
     double tol;              /* KKT tolerance relative to max||a_i||_1 * ||c||; <= 0 -> default
-                                (1e-12 in f64 compute, 2e-6 in f32 compute)                    */
+                                1e-12 (the residuals are float64 in both compute modes)        */
     int64_t cap_rows;        /* scratch sizing: max general (non-singleton) rows per instance;
                                 <= 0 -> m_max                                                  */
     int64_t cap_nnz;         /* scratch sizing: max non-zeros in those rows; <= 0 -> cap_rows*d */
     int32_t warm_pack;       /* 1: `pack` already holds cave_pack() output for this A          */
     int32_t reserved;
+    /* Device-resident dataset (optional, needs warm_pack): `pack` was built by cave_pack() over ALL
+     * n_packed instances of a dataset ([n_packed, m_max, d]); instance b of this call is dataset instance
+     * inst_index[b] (device pointer, int32[B], values in [0, n_packed)).  `A` is then the dataset tensor,
+     * or NULL if it is not resident (instances whose general rows did not fit the packed CSR report
+     * CAVE_ST_NOSPACE).  Replaces DataLoader + collate_fn re-padding every batch (src/dataset.py:133-144). */
+    const int32_t* inst_index;
+    int64_t n_packed;        /* 0 / ignored unless inst_index is set                                   */
 } cave_solver_opts;
 
 typedef struct cave_limits {

@@ -268,3 +268,34 @@ def test_reproducible_at_scale_and_against_kernel_source_on_cpu(precision):
                                compute_f32=precision == "fp32")
     np.testing.assert_allclose(runs[0]["proj"][:n].cpu().numpy(), ref["proj"], rtol=1e-9, atol=1e-10)
     np.testing.assert_array_equal(runs[0]["iters"][:n].cpu().numpy(), ref["iters"])
+
+
+def test_device_resident_dataset_index_matches_dense_batches():
+    """§8f-1: pack the whole dataset once, then address batches by instance index (no dense batch tensor, no
+    scan pass).  Must equal the dense-batch call on the gathered rows, with and without the dense tensor."""
+    from cave_b200 import EPO, cave_forward_backward, innerConeAlignedCosine, pack_constraints, synth
+    dev = _cuda()
+    insts = synth.make_batch("vrp20", 40, seed=31)
+    allc = synth.densify(insts, device=dev)
+    pk = pack_constraints(allc)
+    idx = torch.tensor([7, 3, 39, 0, 3, 21, 12], dtype=torch.int32, device=dev)
+    pred = torch.tensor(synth.predictions(insts, 31, "near"), device=dev)[idx.long()]
+    ref = cave_forward_backward(pred, allc[idx.long()].contiguous(), -1.0, 1, 0.2, "none", want_proj=True, want_status=True)
+    for ctrs in (allc, None):
+        out = cave_forward_backward(pred, ctrs, -1.0, 1, 0.2, "none", want_proj=True, want_status=True, pack=pk, index=idx)
+        for k in ("loss", "grad", "proj", "rnorm", "status"):
+            assert torch.equal(out[k], ref[k]), k
+    pk2 = pack_constraints(allc, keep_dense=False)
+
+    class M:
+        modelSense = EPO.MINIMIZE
+    p = pred.clone().requires_grad_(True)
+    loss = innerConeAlignedCosine(M(), solver="cuda", seed=0, reduction="none")(p, pk2, index=idx)
+    loss.sum().backward()
+    assert torch.allclose(loss, ref["loss"]) and torch.allclose(p.grad, ref["grad"])
+    # dense general rows do not fit the packed CSR: with the dense tensor dropped they must report, not guess
+    A = torch.randn(3, 30, 3000, device=dev)
+    pkd = pack_constraints(A, keep_dense=False)
+    out = cave_forward_backward(torch.randn(2, 3000, device=dev), None, -1.0, 0, want_status=True, pack=pkd,
+                                index=torch.tensor([2, 0], dtype=torch.int32, device=dev))
+    assert ((out["status"] & 0xff) == 3).all() and torch.isnan(out["loss"]).all()

@@ -12,7 +12,7 @@ CAVE_OK = 0
 MODE_EXACT, MODE_INNER, MODE_HEURISTIC = 0, 1, 2
 REDUCE = {"mean": 0, "sum": 1, "none": 2}
 F32, F64 = 0, 1
-ST_CONVERGED, ST_ITER_CAP, ST_STALLED, ST_NOSPACE, ST_SKIPPED, ST_PATH_LH = 0, 1, 2, 3, 4, 0x100
+ST_CONVERGED, ST_ITER_CAP, ST_STALLED, ST_NOSPACE, ST_SKIPPED, ST_BADINPUT, ST_PATH_LH = 0, 1, 2, 3, 4, 5, 0x100
 
 EXPORTS = ("cave_abi_version", "cave_last_error", "cave_get_limits", "cave_pack_bytes",
            "cave_scratch_bytes", "cave_pack", "cave_forward_backward")

@@ -38,7 +38,7 @@ typedef float4 f4_t;
 typedef ulonglong2 hash_t;
 #endif
 
-enum { ST_CONVERGED = 0, ST_ITER_CAP = 1, ST_STALLED = 2, ST_NOSPACE = 3, ST_SKIPPED = 4, ST_PATH_LH = 0x100 };
+enum { ST_CONVERGED = 0, ST_ITER_CAP = 1, ST_STALLED = 2, ST_NOSPACE = 3, ST_SKIPPED = 4, ST_BADINPUT = 5, ST_PATH_LH = 0x100 };
 enum { MODE_EXACT = 0, MODE_INNER = 1, MODE_HEURISTIC = 2 };
 
 struct SolveOpts {
@@ -998,7 +998,9 @@ CAVE_DEV bool solve_instance_t(Ctx& cx, const Instance& in, Arena& ar, const TIO
         for (int k = cx.tid; k < d; k += cx.nthr) { T v = (T)(ep.sign * (double)pred[k]); c[k] = v; r[k] = v; cc += v * v; }
         cc = cx.block_sum(cc);
         const T cnorm = (T)sqrt((double)cc);
-        const bool solve = ep.mode != MODE_HEURISTIC && !empty;
+        const bool finite_in = cc < (T)1e300;              // false for NaN / Inf predictions
+        const bool solve = ep.mode != MODE_HEURISTIC && !empty && finite_in;
+        if (!finite_in) res.status = ST_BADINPUT;
         if (solve && in.ngen > 0) {
             if (in.nsingc == 0) lh_solve<T, TH>(cx, in, ar, c.raw(), r.raw(), cnorm, opt, res);
             else newton_solve<T, TH, HOT>(cx, in, ar, c, r, rt, cnorm, opt, res);

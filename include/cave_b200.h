@@ -62,6 +62,7 @@ extern "C" {
 #define CAVE_ST_STALLED 2       /* line search could not make progress                     */
 #define CAVE_ST_NOSPACE 3       /* instance exceeds scratch caps; outputs are NaN          */
 #define CAVE_ST_SKIPPED 4       /* heuristic mode or empty cone: no solve was needed       */
+#define CAVE_ST_BADINPUT 5      /* NaN / Inf in the prediction: no solve, outputs are NaN  */
 #define CAVE_ST_PATH_LH 0x100   /* flag: solved by the Lawson-Hanson path (else Newton)    */
 
 typedef struct cave_solver_opts {

@@ -299,3 +299,20 @@ def test_device_resident_dataset_index_matches_dense_batches():
     out = cave_forward_backward(torch.randn(2, 3000, device=dev), None, -1.0, 0, want_status=True, pack=pkd,
                                 index=torch.tensor([2, 0], dtype=torch.int32, device=dev))
     assert ((out["status"] & 0xff) == 3).all() and torch.isnan(out["loss"]).all()
+
+
+def test_status_words_report_caps_and_bad_input():
+    from cave_b200 import cave_forward_backward, synth
+    dev = _cuda()
+    insts = synth.make_batch("tsp20", 4, seed=41)
+    A = synth.densify(insts, device=dev)
+    pred = torch.tensor(synth.predictions(insts, 41, "near"), dtype=torch.float64, device=dev)
+    out = cave_forward_backward(pred, A, -1.0, 1, 0.2, "none", want_status=True, max_iter=1)
+    assert ((out["status"] & 0xff) == 1).all() and (out["iters"] == 1).all()      # iteration cap, best iterate
+    assert torch.isfinite(out["loss"]).all() and torch.isfinite(out["grad"]).all()
+    bad = pred.clone()
+    bad[2, 5] = float("nan")
+    out = cave_forward_backward(bad, A, -1.0, 1, 0.2, "none", want_status=True)
+    st = (out["status"] & 0xff).cpu().tolist()
+    assert st[2] == 5 and st[0] == 0 and st[1] == 0 and st[3] == 0
+    assert torch.isnan(out["loss"][2]) and torch.isfinite(out["loss"][[0, 1, 3]]).all()

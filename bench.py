@@ -273,7 +273,7 @@ def run_ours(args):
             p.grad = None
             loss = mod(p, A_host)        # H2D of pred_cost and tight_ctrs inside; loss and grad come back to host
             loss.backward()
-            return float(loss)
+            return loss.item()
 
         e2e_step()
         n_e2e = max(2, min(args.steps, 5))
@@ -299,7 +299,7 @@ def run_ours(args):
             p.grad = None
             loss = mod(p, pack, index=perm_host)       # H2D: pred_cost + index; D2H: loss + gradient
             loss.backward()
-            return float(loss)
+            return loss.item()
 
         e2e_resident_step()
         n_res = max(3, args.steps)

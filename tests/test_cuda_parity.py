@@ -316,3 +316,16 @@ def test_status_words_report_caps_and_bad_input():
     st = (out["status"] & 0xff).cpu().tolist()
     assert st[2] == 5 and st[0] == 0 and st[1] == 0 and st[3] == 0
     assert torch.isnan(out["loss"][2]) and torch.isfinite(out["loss"][[0, 1, 3]]).all()
+
+
+def test_training_loop_reduces_the_loss():
+    """code_sample.py analogue (linear predictor, CaVE+, Adam) on synthetic TSP-20 with the device-resident
+    dataset: the loss must go down — exercises autograd, the index path and repeated calls end to end."""
+    import importlib.util
+    _cuda()
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "train_tsp20_cave_plus.py")
+    spec = importlib.util.spec_from_file_location("train_example", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    hist = mod.train(num_data=128, epochs=6, batch=32, verbose=False)
+    assert np.isfinite(hist).all() and hist[-1] < 0.6 * hist[0], hist

@@ -73,6 +73,13 @@ struct Arena {
         overflow = true;
         return (U*)gl;
     }
+    // setup-only scratch: always from the global slot (keeps shared memory for the iteration's arrays)
+    template <class U> CAVE_DEV U* get_gl(size_t n) {
+        const size_t bytes = (n * sizeof(U) + 15) & ~(size_t)15;
+        if (gl_off + bytes <= gl_cap) { U* p = (U*)(gl + gl_off); gl_off += bytes; return p; }
+        overflow = true;
+        return (U*)gl;
+    }
     template <bool HOT, class U> CAVE_DEV HPtr<U, HOT> geth(size_t n) {
         if (HOT) return HPtr<U, HOT>(get_sm<U>(n));
         return HPtr<U, HOT>(get<U>(n));
@@ -85,6 +92,8 @@ template <class T> CAVE_DEV bool psi_active(T r, int t) {
 }
 template <class T> CAVE_DEV T psi(T r, int t) { return psi_active(r, t) ? r : (T)0; }
 template <class T> CAVE_DEV T cabs(T v) { return v < (T)0 ? -v : v; }
+// start of row i in a row-packed lower triangle (row i holds columns 0..i)
+CAVE_DEV uint32_t tri(int i) { return ((uint32_t)i * (uint32_t)(i + 1)) >> 1; }
 // reciprocal of a positive pivot without a full-precision division on the critical path
 CAVE_DEV float fast_rcp(float x) { return 1.0f / x; }
 CAVE_DEV double fast_rcp(double x) {
@@ -161,13 +170,13 @@ CAVE_DEV void chol_solve(Ctx& cx, const T* L, int n, int ld, const T* diagL, T* 
 
 
 // ------------------------------------------------------------------ blocked LDL^T (Newton systems)
-// In-place LDL^T of the lower triangle of L[0..nf) with unscaled columns (S_ik = l_ik d_k) and one
+// In-place LDL^T of the row-packed lower triangle L (row i at tri(i)) with unscaled columns (S_ik = l_ik d_k) and one
 // extra row L[nf] holding the right-hand side, which the elimination turns into z = L^-1 g.
 // invd[j] receives 1/d_j.  Panels of 8 columns: warp 0 factors a panel entirely in registers
 // (rows on lanes, shuffles for the pivot column), then all warps apply the rank-8 update to the
 // trailing block — two CTA barriers per panel instead of one or two per column.
 template <class TH, class PL>
-CAVE_DEV void ldlt_blocked(Ctx& cx, PL L, int nf, int ldl, PL invd, TH piv_floor) {
+CAVE_DEV void ldlt_blocked(Ctx& cx, PL L, int nf, PL invd, TH piv_floor) {
     constexpr int PB = 8;
     if (nf + 1 <= 2 * Ctx::WS || Ctx::WS == 1) {
         for (int j0 = 0; j0 < nf; j0 += PB) {
@@ -177,13 +186,13 @@ CAVE_DEV void ldlt_blocked(Ctx& cx, PL L, int nf, int ldl, PL invd, TH piv_floor
                 // single-thread restatement of the panel factorisation
                 for (int jj = 0; jj < pw; ++jj) {
                     const int j = j0 + jj;
-                    TH dj = L[(size_t)j * ldl + j];
+                    TH dj = L[tri(j) + j];
                     const TH inv = (TH)1 / (dj > piv_floor ? dj : piv_floor);
                     invd[j] = inv;
                     for (int i = j + 1; i <= nf; ++i) {
-                        const TH f = (TH)L[(size_t)i * ldl + j] * inv;
+                        const TH f = (TH)L[tri(i) + j] * inv;
                         for (int c = jj + 1; c < pw; ++c)
-                            if (j0 + c <= i || i == nf) L[(size_t)i * ldl + j0 + c] -= f * (TH)L[(size_t)(j0 + c) * ldl + j];
+                            if (j0 + c <= i || i == nf) L[tri(i) + j0 + c] -= f * (TH)L[tri(j0 + c) + j];
                     }
                 }
 #else
@@ -193,7 +202,7 @@ CAVE_DEV void ldlt_blocked(Ctx& cx, PL L, int nf, int ldl, PL invd, TH piv_floor
                     const int i = j0 + cx.lane + 32 * s;
 #pragma unroll
                     for (int c = 0; c < PB; ++c)
-                        a[s][c] = (i <= nf && c < pw && (j0 + c <= i || i == nf)) ? (TH)L[(size_t)i * ldl + j0 + c] : (TH)0;
+                        a[s][c] = (i <= nf && c < pw && (j0 + c <= i || i == nf)) ? (TH)L[tri(i) + j0 + c] : (TH)0;
                 }
 #pragma unroll
                 for (int jj = 0; jj < PB; ++jj) {
@@ -221,7 +230,7 @@ CAVE_DEV void ldlt_blocked(Ctx& cx, PL L, int nf, int ldl, PL invd, TH piv_floor
                     const int i = j0 + cx.lane + 32 * s;
 #pragma unroll
                     for (int c = 0; c < PB; ++c)
-                        if (i <= nf && c < pw && (j0 + c <= i || i == nf)) L[(size_t)i * ldl + j0 + c] = a[s][c];
+                        if (i <= nf && c < pw && (j0 + c <= i || i == nf)) L[tri(i) + j0 + c] = a[s][c];
                 }
 #endif
             }
@@ -234,9 +243,9 @@ CAVE_DEV void ldlt_blocked(Ctx& cx, PL L, int nf, int ldl, PL invd, TH piv_floor
                     const bool kin = k <= nf - 1;
                     TH pk[PB];
 #pragma unroll
-                    for (int c = 0; c < PB; ++c) pk[c] = (kin && c < pw) ? (TH)L[(size_t)k * ldl + j0 + c] * (TH)invd[j0 + c] : (TH)0;
+                    for (int c = 0; c < PB; ++c) pk[c] = (kin && c < pw) ? (TH)L[tri(k) + j0 + c] * (TH)invd[j0 + c] : (TH)0;
                     for (int i = kc + cx.warp; i <= nf; i += cx.nwarp) {
-                        const PL li = L + (size_t)i * ldl;
+                        const PL li = L + tri(i);
                         if (kin && (k <= i || i == nf)) {
                             TH x = li[k];
                             TH f[PB];
@@ -256,13 +265,13 @@ CAVE_DEV void ldlt_blocked(Ctx& cx, PL L, int nf, int ldl, PL invd, TH piv_floor
     // generic path (nf >= 64): one column at a time
     for (int j = 0; j < nf; ++j) {
         cx.sync();
-        TH dj = L[(size_t)j * ldl + j];
+        TH dj = L[tri(j) + j];
         const TH inv = (TH)1 / (dj > piv_floor ? dj : piv_floor);
         if (cx.tid == 0) invd[j] = inv;
         for (int i = j + 1 + cx.warp; i <= nf; i += cx.nwarp) {
-            const TH lij = (TH)L[(size_t)i * ldl + j] * inv;
+            const TH lij = (TH)L[tri(i) + j] * inv;
             const int kend = i < nf ? i : nf - 1;
-            for (int k = j + 1 + cx.lane; k <= kend; k += Ctx::WS) L[(size_t)i * ldl + k] -= lij * (TH)L[(size_t)k * ldl + j];
+            for (int k = j + 1 + cx.lane; k <= kend; k += Ctx::WS) L[tri(i) + k] -= lij * (TH)L[tri(k) + j];
         }
     }
     cx.sync();
@@ -291,10 +300,11 @@ struct Result {
 };
 
 // ------------------------------------------------------------------ Newton path
-template <class T, class TH, bool HOT>
+template <class T, class TH, class TC, bool HOT>
 struct NewtonWork {
     int d, mB, nv;
-    HPtr<T, HOT> c, r, rt;
+    HPtr<TC, HOT> c;                              // c = sign * pred, exact in the I/O dtype
+    HPtr<T, HOT> r;
     HPtr<uint8_t, HOT> ctype;
     int* rptr; uint16_t* rcol; void* rval;       // CSR of the general rows (values float, or int8 if i8)
     bool i8;
@@ -313,12 +323,12 @@ struct NewtonWork {
     HPtr<TH, HOT> xs;                             // [nv] Newton step on the free set, then 1/d_j
 };
 
-template <class VT, class T, class TH, bool HOT>
-CAVE_DEV void nw_eval2_t(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> nu, HPtr<T, HOT> rout, T& f, T& extra) {
+template <class VT, class T, class TH, class TC, bool HOT>
+CAVE_DEV void nw_eval2_t(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HOT> nu, HPtr<T, HOT> rout, T& f, T& extra) {
     const VT* cval = (const VT*)W.cval;
     T acc = (T)0;
     for (int k = cx.tid; k < W.d; k += cx.nthr) {
-        T rk = W.c[k];
+        T rk = (T)(TC)W.c[k];
         for (int e = W.cptr[k]; e < W.cptr[k + 1]; ++e) rk -= (T)cval[e] * (T)nu[W.crow[e]];
         rout[k] = rk;
         T q = psi(rk, (int)(uint8_t)W.ctype[k]);
@@ -327,13 +337,13 @@ CAVE_DEV void nw_eval2_t(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> 
     cx.block_sum2(acc, extra);
     f = (T)0.5 * acc;
 }
-template <class T, class TH, bool HOT>
-CAVE_DEV void nw_eval2(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> nu, HPtr<T, HOT> rout, T& f, T& extra) {
+template <class T, class TH, class TC, bool HOT>
+CAVE_DEV void nw_eval2(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HOT> nu, HPtr<T, HOT> rout, T& f, T& extra) {
     if (W.i8) nw_eval2_t<int8_t>(cx, W, nu, rout, f, extra); else nw_eval2_t<float>(cx, W, nu, rout, f, extra);
 }
 
-template <class VT, class T, class TH, bool HOT>
-CAVE_DEV void nw_grad_t(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> r, HPtr<T, HOT> g) {
+template <class VT, class T, class TH, class TC, bool HOT>
+CAVE_DEV void nw_grad_t(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HOT> r, HPtr<T, HOT> g) {
     const VT* rval = (const VT*)W.rval;
     for (int v = cx.warp; v < W.nv; v += cx.nwarp) {
         int row = W.vrow[v];
@@ -347,16 +357,16 @@ CAVE_DEV void nw_grad_t(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> r
     }
     cx.sync();
 }
-template <class T, class TH, bool HOT>
-CAVE_DEV void nw_grad(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> r, HPtr<T, HOT> g) {
+template <class T, class TH, class TC, bool HOT>
+CAVE_DEV void nw_grad(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HOT> r, HPtr<T, HOT> g) {
     if (W.i8) nw_grad_t<int8_t>(cx, W, r, g); else nw_grad_t<float>(cx, W, r, g);
 }
 
 // Fold the columns whose activity psi'(r_k) changed since the last call into H = B W B^T
 // (lower triangle over ALL variables): H += +-b_k b_k^T with shared-memory atomics.  After the
 // first iterations only a handful of coordinates change sign, so this is almost free.
-template <class VT, class T, class TH, bool HOT>
-CAVE_DEV void nw_hessian_update_t(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> r) {
+template <class VT, class T, class TH, class TC, bool HOT>
+CAVE_DEV void nw_hessian_update_t(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HOT> r) {
     const VT* cval = (const VT*)W.cval;
     const int nv = W.nv;
     for (int k = cx.tid; k < W.d; k += cx.nthr) {
@@ -371,14 +381,14 @@ CAVE_DEV void nw_hessian_update_t(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr
             for (int e2 = s; e2 <= e1; ++e2) {
                 const int b = W.crow[e2];
                 const int hi = a > b ? a : b, lo = a > b ? b : a;
-                W.H.atomic_add((size_t)hi * nv + lo, va * (TH)cval[e2]);
+                W.H.atomic_add(tri(hi) + lo, va * (TH)cval[e2]);
             }
         }
     }
     cx.sync();
 }
-template <class T, class TH, bool HOT>
-CAVE_DEV void nw_hessian_update(Ctx& cx, const NewtonWork<T, TH, HOT>& W, HPtr<T, HOT> r) {
+template <class T, class TH, class TC, bool HOT>
+CAVE_DEV void nw_hessian_update(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HOT> r) {
     if (W.i8) nw_hessian_update_t<int8_t>(cx, W, r); else nw_hessian_update_t<float>(cx, W, r);
 }
 
@@ -403,8 +413,8 @@ CAVE_DEV void warp0_inclusive_scan(Ctx& cx, int* x, int n) {
 // general rows into the arena (from the scan kernel's pack, or by reading the rows of A when the pack
 // could not hold them) and build the CSC.  HOT selects shared-memory-only allocation for the arrays of
 // the Newton iteration.  Returns false if the instance does not fit (ar.hot_overflow tells which side).
-template <class T, class TH, bool HOT>
-CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH, HOT>& W, T* maxrow_l1, T* maxrow_l2sq) {
+template <class T, class TH, class TC, bool HOT>
+CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH, TC, HOT>& W, T* maxrow_l1, T* maxrow_l2sq) {
     const int d = in.d, mB = in.ngen;
     W.d = d; W.mB = mB;
     // hot: vectors of the iteration
@@ -417,16 +427,17 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     HPtr<uint8_t, HOT> ctype_s = ar.geth<HOT, uint8_t>(d + 1);
     // cold: setup scratch and sparse structure
     W.rptr = ar.get<int>(mB + 2);
-    int* goff = ar.get<int>(mB + 2);              // row offsets in the source CSR (pack, or the one built here)
-    int* gcnt = ar.get<int>(mB + 2);              // non-zeros per general row
-    W.grow = ar.get<int>(mB + 1);
-    W.rtype = ar.get<uint8_t>(mB + 1);
+    // cold, setup only (global slot)
+    int* goff = ar.get_gl<int>(mB + 2);           // row offsets in the source CSR (pack, or the one built here)
+    int* gcnt = ar.get_gl<int>(mB + 2);           // non-zeros per general row
+    W.grow = ar.get_gl<int>(mB + 1);
+    W.rtype = ar.get_gl<uint8_t>(mB + 1);
     W.vrow = ar.get<int>(mB + 1);
-    uint64_t* hpos = ar.get<uint64_t>(mB + 1);
-    uint64_t* hneg = ar.get<uint64_t>(mB + 1);
-    int* cand = ar.get<int>(mB + 1);
+    uint64_t* hpos = ar.get_gl<uint64_t>(mB + 1);
+    uint64_t* hneg = ar.get_gl<uint64_t>(mB + 1);
+    int* cand = ar.get_gl<int>(mB + 1);
+    W.cur = ar.get_gl<int>(d + 1);
     W.cptr = ar.get<int>(d + 2);
-    W.cur = ar.get<int>(d + 1);
     if (ar.overflow) return false;
     cx.phase(1);
     for (int k = cx.tid; k < d; k += cx.nthr) { ctype_s[k] = in.ctype[k]; W.wflag[k] = 0; }
@@ -553,8 +564,8 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     const int nnzc = W.flist[1];
     cx.sync();
     const int nv = W.nv;
-    W.H = ar.geth<HOT, TH>((size_t)nv * nv + 1);
-    W.L = ar.geth<HOT, TH>((size_t)(nv + 1) * ((nv + 1) | 1) + 1);
+    W.H = ar.geth<HOT, TH>((size_t)tri(nv) + 1);                 // row-packed lower triangles
+    W.L = ar.geth<HOT, TH>((size_t)tri(nv + 2) + 1);
     // the CSC feeds eval (several times per iteration) and the Hessian update, the CSR only the gradient:
     // the CSC gets shared memory first.  Integer-valued rows (every shipped model) are kept as int8.
     W.i8 = (in.csr_ok & 3) == 3;
@@ -586,7 +597,7 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     cx.phase(4);
     // CSC: count, scan, fill with a cursor, then order every column by variable id
     for (int k = cx.tid; k <= d; k += cx.nthr) W.cptr[k] = 0;
-    for (size_t t = cx.tid; t < (size_t)nv * nv; t += cx.nthr) W.H[t] = (TH)0;
+    for (uint32_t t = cx.tid; t < tri(nv); t += cx.nthr) W.H[t] = (TH)0;
     cx.sync();
     for (int v = cx.warp; v < nv; v += cx.nwarp) {
         int row = W.vrow[v];
@@ -626,13 +637,13 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     return true;
 }
 
-template <class T, class TH, bool HOT>
-CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<T, HOT> c, HPtr<T, HOT> r, HPtr<T, HOT> rt, T cnorm,
+template <class T, class TH, class TC, bool HOT>
+CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<TC, HOT> c, HPtr<T, HOT> r, T cnorm,
                            const SolveOpts& opt, Result<T>& out) {
-    NewtonWork<T, TH, HOT> W;
-    W.c = c; W.r = r; W.rt = rt;
+    NewtonWork<T, TH, TC, HOT> W;
+    W.c = c; W.r = r;
     T l1max, l2max;
-    if (!nw_setup<T, TH, HOT>(cx, in, ar, W, &l1max, &l2max)) { out.status = ST_NOSPACE; out.iters = 0; out.r = r.raw(); return; }
+    if (!nw_setup<T, TH, TC, HOT>(cx, in, ar, W, &l1max, &l2max)) { out.status = ST_NOSPACE; out.iters = 0; out.r = r.raw(); return; }
     const int nv = W.nv;
     const T scale = (l1max > (T)1 ? l1max : (T)1) * (cnorm > (T)1e-30 ? cnorm : (T)1e-30);
     const T tol = (T)(opt.tol > 0 ? opt.tol : 1e-12) * scale;   // tight: the rnorm < 1e-7 inside-the-cone test depends on it
@@ -644,7 +655,8 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<T, HOT> 
 
     for (int v = cx.tid; v < nv; v += cx.nthr) W.nu[v] = (T)0;
     cx.sync();
-    HPtr<T, HOT> nu = W.nu, nut = W.nut, rc = W.r, rn = W.rt;
+    HPtr<T, HOT> nu = W.nu, nut = W.nut;
+    const HPtr<T, HOT> rc = W.r;       // r is updated in place by every trial evaluation
     cx.phase(5);
     T f, dummy = (T)0;
     nw_eval2(cx, W, nu, rc, f, dummy);
@@ -683,31 +695,30 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<T, HOT> 
         cx.phase(8);
         nw_hessian_update(cx, W, rc);          // (ends with a barrier: flist / fpos visible too)
         const int nf = (int)W.fpos[nv];
-        const int ldl = (nf + 1) | 1;
         cx.phase(9);
         // L <- [H_FF + reg I ; g_F^T]
         for (int a = cx.warp; a <= nf; a += cx.nwarp) {
-            const HPtr<TH, HOT> la = W.L + (size_t)a * ldl;
+            const HPtr<TH, HOT> la = W.L + tri(a);
             if (a == nf) {
                 for (int b = cx.lane; b < nf; b += Ctx::WS) la[b] = (TH)(T)W.g[(int)W.flist[b]];
             } else {
-                const HPtr<TH, HOT> ha = W.H + (size_t)(int)W.flist[a] * nv;    // flist ascending => flist[a] >= flist[b]
+                const HPtr<TH, HOT> ha = W.H + tri((int)W.flist[a]);            // flist ascending => flist[a] >= flist[b]
                 for (int b = cx.lane; b <= a; b += Ctx::WS) la[b] = (TH)ha[(int)W.flist[b]] + (a == b ? reg : (TH)0);
             }
         }
         cx.sync();
         cx.phase(10);
         const HPtr<TH, HOT> invd = W.xs + (nv + 2);
-        ldlt_blocked<TH, HPtr<TH, HOT> >(cx, W.L, nf, ldl, invd, piv_floor);
+        ldlt_blocked<TH, HPtr<TH, HOT> >(cx, W.L, nf, invd, piv_floor);
         cx.phase(11);
         // back substitution D L^T x = z by warp 0 (column oriented, no reductions, no divisions)
         if (cx.warp == 0) {
-            const HPtr<TH, HOT> z = W.L + (size_t)nf * ldl;
+            const HPtr<TH, HOT> z = W.L + tri(nf);
             for (int j = nf - 1; j >= 0; --j) {
                 const TH xj = (TH)z[j] * (TH)invd[j];
                 cx.syncwarp();
                 if (cx.lane == 0) W.xs[j] = xj;
-                for (int i = cx.lane; i < j; i += Ctx::WS) z[i] -= (TH)W.L[(size_t)j * ldl + i] * xj;
+                for (int i = cx.lane; i < j; i += Ctx::WS) z[i] -= (TH)W.L[tri(j) + i] * xj;
                 cx.syncwarp();
             }
         }
@@ -728,13 +739,17 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<T, HOT> 
                 dec += (T)W.g[v] * (nv_ - t);
             }
             cx.sync();
-            nw_eval2(cx, W, nut, rn, ft, dec);
+            nw_eval2(cx, W, nut, rc, ft, dec);
             if (ft <= f - (T)1e-4 * dec + (T)4 * eps_mach<T>() * f) { ok = true; break; }
             alpha *= (T)0.5;
         }
-        if (!ok) { status = ST_STALLED; break; }
+        if (!ok) {                    // r holds the last rejected trial: restore it for the current iterate
+            T d0 = (T)0;
+            nw_eval2(cx, W, nu, rc, f, d0);
+            status = ST_STALLED;
+            break;
+        }
         HPtr<T, HOT> t1 = nu; nu = nut; nut = t1;
-        HPtr<T, HOT> t2 = rc; rc = rn; rn = t2;
         f = ft;
     }
     cx.phase(13);
@@ -936,12 +951,12 @@ struct EpiParams {
 
 template <class T, class TIO, class PC>
 CAVE_DEV void epilogue(Ctx& cx, const Instance& in, const EpiParams& ep, PC c, const T* r,
-                       bool have_proj, bool empty_cone, T* tbuf,
+                       bool have_proj, bool empty_cone,
                        TIO* grad_out, TIO* proj_out, double* loss_out, double* rnorm_out) {
     const int d = in.d;
     double pp = 0.0, qq = 0.0, cc = 0.0;
     for (int k = cx.tid; k < d; k += cx.nthr) {
-        double ck = (double)(T)c[k];
+        double ck = (double)c[k];
         double q = (have_proj && !empty_cone) ? (double)psi(r[k], (int)in.ctype[k]) : 0.0;
         double p = ck - q;
         pp += p * p; qq += q * q; cc += ck * ck;
@@ -952,18 +967,19 @@ CAVE_DEV void epilogue(Ctx& cx, const Instance& in, const EpiParams& ep, PC c, c
     const double cden = cnorm > 1e-8 ? cnorm : 1e-8;
     const double rr = ep.inner_ratio;
     const bool push = ep.mode == MODE_INNER && !(rnorm < 1e-7);
+    // target t_k (recomputed in the last pass instead of being stored: no d-vector of scratch)
+    auto target = [&](int k, double ck) -> double {
+        if (ep.mode == MODE_HEURISTIC) return (1.0 - rr) * (ck / cden) + rr * (double)in.avg[k];
+        const double q = empty_cone ? 0.0 : (double)psi(r[k], (int)in.ctype[k]);
+        const double ph = (ck - q) / pden;
+        return push ? (1.0 - rr) * ph + rr * (double)in.avg[k] : ph;
+    };
     double tt = 0.0, ct = 0.0;
     for (int k = cx.tid; k < d; k += cx.nthr) {
-        double ck = (double)(T)c[k], t;
-        if (ep.mode == MODE_HEURISTIC) {
-            t = (1.0 - rr) * (ck / cden) + rr * (double)in.avg[k];
-        } else {
-            double q = empty_cone ? 0.0 : (double)psi(r[k], (int)in.ctype[k]);
-            double ph = (ck - q) / pden;
-            t = push ? (1.0 - rr) * ph + rr * (double)in.avg[k] : ph;
-            if (proj_out) proj_out[k] = (TIO)(ck - q);
-        }
-        tbuf[k] = (T)t;
+        const double ck = (double)c[k];
+        const double t = target(k, ck);
+        if (proj_out && ep.mode != MODE_HEURISTIC)
+            proj_out[k] = (TIO)(ck - (empty_cone ? 0.0 : (double)psi(r[k], (int)in.ctype[k])));
         tt += t * t; ct += ck * t;
     }
     tt = cx.block_sum(tt); ct = cx.block_sum(ct);
@@ -973,8 +989,9 @@ CAVE_DEV void epilogue(Ctx& cx, const Instance& in, const EpiParams& ep, PC c, c
     const double invc = cnorm > 0.0 ? 1.0 / cnorm : 0.0;
     const double gs = ep.gscale * ep.sign;
     for (int k = cx.tid; k < d; k += cx.nthr) {
-        double v = (double)tbuf[k] / tden;
-        double w = (double)(T)c[k] * invc;
+        const double ck = (double)c[k];
+        const double v = target(k, ck) / tden;
+        const double w = ck * invc;
         grad_out[k] = (TIO)(gs * (-(v - cosv * w) / cden));
     }
     if (cx.tid == 0) { *loss_out = 1.0 - cosv; *rnorm_out = (ep.mode == MODE_HEURISTIC) ? 0.0 : rnorm; }
@@ -987,7 +1004,8 @@ CAVE_DEV bool solve_instance_t(Ctx& cx, const Instance& in, Arena& ar, const TIO
                                double* loss_out, double* rnorm_out, int* status_out, int* iters_out) {
     typedef double T;      // state vectors are always double; TH is the Hessian / factor precision
     const int d = in.d;
-    HPtr<T, HOT> c = ar.geth<HOT, T>(d), r = ar.geth<HOT, T>(d), rt = ar.geth<HOT, T>(d);
+    HPtr<TIO, HOT> c = ar.geth<HOT, TIO>(d);      // c = sign * pred is exact in the I/O dtype
+    HPtr<T, HOT> r = ar.geth<HOT, T>(d);
     if (HOT && ar.hot_overflow) return false;         // retry with generic placement
     bool nospace = ar.overflow;                         // cannot even hold the cost vector
     Result<T> res; res.r = r.raw(); res.iters = 0; res.status = ST_SKIPPED;
@@ -995,15 +1013,23 @@ CAVE_DEV bool solve_instance_t(Ctx& cx, const Instance& in, Arena& ar, const TIO
     if (!nospace) {
         cx.phase(0);
         T cc = (T)0;
-        for (int k = cx.tid; k < d; k += cx.nthr) { T v = (T)(ep.sign * (double)pred[k]); c[k] = v; r[k] = v; cc += v * v; }
+        for (int k = cx.tid; k < d; k += cx.nthr) { const TIO vc = (TIO)(ep.sign * (double)pred[k]); const T v = (T)vc; c[k] = vc; r[k] = v; cc += v * v; }
         cc = cx.block_sum(cc);
         const T cnorm = (T)sqrt((double)cc);
         const bool finite_in = cc < (T)1e300;              // false for NaN / Inf predictions
         const bool solve = ep.mode != MODE_HEURISTIC && !empty && finite_in;
         if (!finite_in) res.status = ST_BADINPUT;
         if (solve && in.ngen > 0) {
-            if (in.nsingc == 0) lh_solve<T, TH>(cx, in, ar, c.raw(), r.raw(), cnorm, opt, res);
-            else newton_solve<T, TH, HOT>(cx, in, ar, c, r, rt, cnorm, opt, res);
+            if (in.nsingc == 0) {
+                T* cd = ar.get<T>(d);         // Lawson-Hanson works on a float64 copy of c (generic placement)
+                if (!ar.overflow) {
+                    for (int k = cx.tid; k < d; k += cx.nthr) cd[k] = (T)(TIO)c[k];
+                    cx.sync();
+                }
+                lh_solve<T, TH>(cx, in, ar, cd, r.raw(), cnorm, opt, res);
+            } else {
+                newton_solve<T, TH, TIO, HOT>(cx, in, ar, c, r, cnorm, opt, res);
+            }
         } else if (solve) {
             res.status = ST_CONVERGED;      // only singleton rows: closed form, r = c
         }
@@ -1019,8 +1045,7 @@ CAVE_DEV bool solve_instance_t(Ctx& cx, const Instance& in, Arena& ar, const TIO
         return true;
     }
     cx.phase(14);
-    T* tbuf = (res.r == r.raw()) ? rt.raw() : r.raw();
-    epilogue<T, TIO, HPtr<T, HOT> >(cx, in, ep, c, res.r, ep.mode != MODE_HEURISTIC, empty, tbuf, grad_out, proj_out, loss_out, rnorm_out);
+    epilogue<T, TIO, HPtr<TIO, HOT> >(cx, in, ep, c, res.r, ep.mode != MODE_HEURISTIC, empty, grad_out, proj_out, loss_out, rnorm_out);
     if (cx.tid == 0) { *status_out = res.status; *iters_out = res.iters; }
     return true;
 }

@@ -15,7 +15,7 @@ namespace cave {
 __device__ unsigned long long g_phase_cycles[32];
 
 template <class T, class TIO>
-__global__ void __launch_bounds__(512, 1) solve_kernel(SolveParams p) {
+__global__ void __launch_bounds__(256, 2) solve_kernel(SolveParams p) {
     extern __shared__ __align__(16) char smem[];
     __shared__ double red[64];
     __shared__ int s_b;

@@ -329,3 +329,16 @@ def test_training_loop_reduces_the_loss():
     spec.loader.exec_module(mod)
     hist = mod.train(num_data=128, epochs=6, batch=32, verbose=False)
     assert np.isfinite(hist).all() and hist[-1] < 0.6 * hist[0], hist
+
+
+def test_sp5_end_to_end_regret_config0():
+    """BASELINE.json configs[0]: shortest path 5x5, linear predictor, batch 32, CaVE Exact with solver='cuda';
+    exact DP solver for the regret.  Training must bring the normalised test regret well below the untrained one."""
+    import importlib.util
+    _cuda()
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "train_sp5_regret.py")
+    spec = importlib.util.spec_from_file_location("sp5_example", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    r0, r1 = mod.run("cave-e", n_train=400, n_test=400, epochs=6, verbose=False)
+    assert r1 < 0.5 * r0 and r1 < 0.25, (r0, r1)

@@ -52,7 +52,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(logs))
     if verbose:
         print("\n".join(logs))
-    subprocess.check_call([_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs,
+                           "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
     return LIB
 
 

@@ -178,7 +178,6 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     sp.mode = mode; sp.inner_ratio = inner_ratio; sp.sign = sign;
     sp.gscale = reduction == CAVE_REDUCE_MEAN ? 1.0 / (double)B : 1.0;
     sp.max_iter = opts ? opts->max_iter : 0; sp.max_ls = opts ? opts->max_linesearch : 0; sp.tol = opts ? opts->tol : 0.0;
-    sp.profile = env_int("CAVE_PROFILE", 0);
     sp.inst_index = indexed ? opts->inst_index : nullptr;
     int threads = env_int("CAVE_SOLVE_THREADS", 256);
     if (threads != 128 && threads != 256) threads = 256;
@@ -191,16 +190,6 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     fp.loss = loss; fp.loss_i = loss_i; fp.rnorm = rnorm; fp.status_out = status; fp.iters_out = iters;
     ce = cave::launch_finalize(fp, io_dtype == CAVE_F32, st);
     if (ce != cudaSuccess) return fail(CAVE_ECUDA, "finalize kernel launch failed: %s", cudaGetErrorString(ce));
-    return CAVE_OK;
-}
-
-/* debug aid (not part of the stable ABI): per-phase cycle counters of the solve kernel, filled
- * when the environment variable CAVE_PROFILE=1 is set.  Synchronises the device. */
-int cave_debug_phase_cycles(unsigned long long* out32, int reset) {
-    if (!out32) return fail(CAVE_EINVAL, "out32 is null");
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e == cudaSuccess) e = cave::read_phase_cycles(out32, reset);
-    if (e != cudaSuccess) return fail(CAVE_ECUDA, "phase counter read failed: %s", cudaGetErrorString(e));
     return CAVE_OK;
 }
 

@@ -19,7 +19,6 @@ struct Ctx {
     void sync() {}
     void syncwarp() {}
     void bar_named(int, int) {}
-    void phase(int) {}
     template <class T> T warp_sum(T v) { return v; }
     template <class T> T warp_max(T v) { return v; }
     template <class T> T block_sum(T v) { return v; }
@@ -62,11 +61,6 @@ struct Ctx {
     static constexpr int WS = 32;
     int tid, nthr, lane, warp, nwarp;
     double* red;   // shared scratch: >= 2 * 32 doubles
-    unsigned long long* prof = nullptr;   // optional [32] global cycle counters per phase (debug)
-    long long t_last = 0; int ph_cur = 0;
-    __device__ __forceinline__ void phase(int n) {
-        if (prof && tid == 0) { long long t = clock64(); atomicAdd(prof + ph_cur, (unsigned long long)(t - t_last)); t_last = t; ph_cur = n; }
-    }
     __device__ Ctx(double* red_) : red(red_) {
         tid = threadIdx.x; nthr = blockDim.x; lane = tid & 31; warp = tid >> 5; nwarp = nthr >> 5;
     }

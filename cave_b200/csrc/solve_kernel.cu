@@ -12,15 +12,12 @@
 
 namespace cave {
 
-__device__ unsigned long long g_phase_cycles[32];
-
 template <class T, class TIO>
 __global__ void __launch_bounds__(256, 2) solve_kernel(SolveParams p) {
     extern __shared__ __align__(16) char smem[];
     __shared__ double red[64];
     __shared__ int s_b;
     Ctx cx(red);
-    if (p.profile) { cx.prof = g_phase_cycles; cx.t_last = clock64(); cx.ph_cur = 15; }
     char* slot = p.slots + (size_t)blockIdx.x * p.slot_bytes;
     EpiParams ep; ep.mode = p.mode; ep.inner_ratio = p.inner_ratio; ep.sign = p.sign; ep.gscale = p.gscale;
     SolveOpts opt; opt.max_iter = p.max_iter; opt.max_ls = p.max_ls; opt.tol = p.tol;
@@ -48,7 +45,6 @@ __global__ void __launch_bounds__(256, 2) solve_kernel(SolveParams p) {
                                proj ? proj + (size_t)b * p.d : nullptr, p.loss64 + b, p.rnorm64 + b,
                                p.status + b, p.iters + b);
         __syncthreads();
-        cx.phase(15);
     }
 }
 
@@ -94,15 +90,6 @@ cudaError_t launch_solve(const SolveParams& p, int compute_f32, int io_f32, int 
                                    : launch_solve_t<float, double>(p, grid, threads, stream);
     return io_f32 ? launch_solve_t<double, float>(p, grid, threads, stream)
                   : launch_solve_t<double, double>(p, grid, threads, stream);
-}
-
-cudaError_t read_phase_cycles(unsigned long long* out32, int reset) {
-    cudaError_t e = cudaMemcpyFromSymbol(out32, g_phase_cycles, 32 * sizeof(unsigned long long));
-    if (e == cudaSuccess && reset) {
-        unsigned long long z[32] = {0};
-        e = cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
-    }
-    return e;
 }
 
 cudaError_t launch_finalize(const FinalizeParams& p, int io_f32, cudaStream_t stream) {

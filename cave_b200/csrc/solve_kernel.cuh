@@ -34,7 +34,6 @@ struct SolveParams {
     double inner_ratio, sign, gscale;
     int max_iter, max_ls;
     double tol;
-    int profile;           // accumulate per-phase cycle counters (debug)
     const int* inst_index; // nullable: batch position -> instance of the (dataset-wide) pack and of A
 };
 
@@ -47,7 +46,6 @@ struct FinalizeParams {
 };
 
 cudaError_t launch_solve(const SolveParams& p, int compute_f32, int io_f32, int grid, int threads, cudaStream_t stream);
-cudaError_t read_phase_cycles(unsigned long long* out32, int reset);
 cudaError_t launch_finalize(const FinalizeParams& p, int io_f32, cudaStream_t stream);
 
 }  // namespace cave

@@ -314,6 +314,7 @@ struct NewtonWork {
     HPtr<uint8_t, HOT> vfree;                     // variable is sign-free
     int* cptr; uint16_t* crow; void* cval;       // CSC over variables
     HPtr<T, HOT> nu, g, dir, nut;
+    HPtr<T, HOT> wmax;                            // [32] per-warp partial maxima
     HPtr<int, HOT> flist;                         // free-set variable ids
     HPtr<int, HOT> fpos;                          // variable -> position in flist or -1
     int* cur;                                     // [d] CSC fill cursors (setup only)
@@ -342,9 +343,12 @@ CAVE_DEV void nw_eval2(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HOT
     if (W.i8) nw_eval2_t<int8_t>(cx, W, nu, rout, f, extra); else nw_eval2_t<float>(cx, W, nu, rout, f, extra);
 }
 
+// g = -B psi(r), and in the same pass the projected-gradient fixed-point residual
+// max_v |nu_v - P(nu_v - g_v)| (returned to every thread; one barrier in total)
 template <class VT, class T, class TH, class TC, bool HOT>
-CAVE_DEV void nw_grad_t(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HOT> r, HPtr<T, HOT> g) {
+CAVE_DEV T nw_grad_t(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HOT> r, HPtr<T, HOT> g, HPtr<T, HOT> nu) {
     const VT* rval = (const VT*)W.rval;
+    T wres = (T)0;
     for (int v = cx.warp; v < W.nv; v += cx.nwarp) {
         int row = W.vrow[v];
         T acc = (T)0;
@@ -353,13 +357,22 @@ CAVE_DEV void nw_grad_t(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HO
             acc += (T)rval[e] * psi((T)r[k], (int)(uint8_t)W.ctype[k]);
         }
         acc = cx.warp_sum(acc);
-        if (cx.lane == 0) g[v] = -acc;
+        const T gv = -acc, nv_ = nu[v];
+        if (cx.lane == 0) g[v] = gv;
+        T t = nv_ - gv;
+        if (!(uint8_t)W.vfree[v] && t < (T)0) t = (T)0;
+        const T w = cabs(nv_ - t);
+        wres = w > wres ? w : wres;
     }
+    if (cx.lane == 0) W.wmax[cx.warp] = wres;
     cx.sync();
+    T res = (T)0;
+    for (int w2 = 0; w2 < cx.nwarp; ++w2) { const T x = W.wmax[w2]; res = x > res ? x : res; }
+    return res;
 }
 template <class T, class TH, class TC, bool HOT>
-CAVE_DEV void nw_grad(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HOT> r, HPtr<T, HOT> g) {
-    if (W.i8) nw_grad_t<int8_t>(cx, W, r, g); else nw_grad_t<float>(cx, W, r, g);
+CAVE_DEV T nw_grad(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HOT> r, HPtr<T, HOT> g, HPtr<T, HOT> nu) {
+    return W.i8 ? nw_grad_t<int8_t>(cx, W, r, g, nu) : nw_grad_t<float>(cx, W, r, g, nu);
 }
 
 // Fold the columns whose activity psi'(r_k) changed since the last call into H = B W B^T
@@ -419,7 +432,8 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     W.d = d; W.mB = mB;
     // hot: vectors of the iteration
     W.nu = ar.geth<HOT, T>(mB + 1); W.g = ar.geth<HOT, T>(mB + 1); W.dir = ar.geth<HOT, T>(mB + 1); W.nut = ar.geth<HOT, T>(mB + 1);
-    W.xs = ar.geth<HOT, TH>(2 * mB + 6);          // Newton step, then reciprocal pivots
+    W.xs = ar.geth<HOT, TH>(2 * mB + 6);          // reciprocal pivots (and scratch)
+    W.wmax = ar.geth<HOT, T>(32);
     W.flist = ar.geth<HOT, int>(mB + 2);
     W.fpos = ar.geth<HOT, int>(mB + 2);
     W.vfree = ar.geth<HOT, uint8_t>(mB + 1);
@@ -439,7 +453,6 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     W.cur = ar.get_gl<int>(d + 1);
     W.cptr = ar.get<int>(d + 2);
     if (ar.overflow) return false;
-    cx.phase(1);
     for (int k = cx.tid; k < d; k += cx.nthr) { ctype_s[k] = in.ctype[k]; W.wflag[k] = 0; }
     W.ctype = ctype_s;
     for (int i = cx.tid; i < mB; i += cx.nthr) {
@@ -505,7 +518,6 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     } else {
         *maxrow_l1 = (T)in.maxl1; *maxrow_l2sq = (T)in.maxl2;
     }
-    cx.phase(2);
     // merge b_j = -b_i : cand[i] = smallest j != i with row_j == -row_i (hash match, then an exact
     // comparison); merged iff the choice is mutual.  One warp per row.
     for (int i = cx.warp; i < mB; i += cx.nwarp) {
@@ -539,7 +551,6 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
         W.rtype[i] = (j >= 0 && cand[j] == i) ? (i < j ? 1 : 2) : 0;
     }
     cx.sync();
-    cx.phase(3);
     // variables = rows that were not dropped (ordered compaction by warp 0).  With a packed CSR only the
     // kept rows are copied in (rptr over variables, vrow = identity); in fallback mode the CSR holds every
     // general row and vrow maps a variable to its row.
@@ -594,7 +605,6 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
         for (int i = cx.tid; i < mB; i += cx.nthr) W.rptr[i] = goff[i];
         if (cx.tid == 0) W.rptr[mB] = goff[mB - 1] + gcnt[mB - 1];
     }
-    cx.phase(4);
     // CSC: count, scan, fill with a cursor, then order every column by variable id
     for (int k = cx.tid; k <= d; k += cx.nthr) W.cptr[k] = 0;
     for (uint32_t t = cx.tid; t < tri(nv); t += cx.nthr) W.H[t] = (TH)0;
@@ -657,45 +667,50 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<TC, HOT>
     cx.sync();
     HPtr<T, HOT> nu = W.nu, nut = W.nut;
     const HPtr<T, HOT> rc = W.r;       // r is updated in place by every trial evaluation
-    cx.phase(5);
     T f, dummy = (T)0;
     nw_eval2(cx, W, nu, rc, f, dummy);
     int status = ST_ITER_CAP, it = 0;
     for (; it < max_iter; ++it) {
-        cx.phase(6);
-        nw_grad(cx, W, rc, W.g);
-        T res = (T)0;
-        for (int v = cx.tid; v < nv; v += cx.nthr) {
-            const T nv_ = nu[v];
-            T t = nv_ - (T)W.g[v];
-            if (!(uint8_t)W.vfree[v] && t < (T)0) t = (T)0;
-            T w = cabs(nv_ - t);
-            res = w > res ? w : res;
-        }
-        res = cx.block_max(res);
+        const T res = nw_grad(cx, W, rc, W.g, nu);
         if (!(res > tol)) { status = ST_CONVERGED; break; }
-        cx.phase(7);
         const T epsb = res < (T)1e-3 ? res : (T)1e-3;
-        // ordered free list (every variable that is not epsilon-binding), built by warp 0
-        if (cx.warp == 0) {
-            int nfb = 0;
-            for (int v0 = 0; v0 < nv; v0 += Ctx::WS) {
-                const int v = v0 + cx.lane;
+        // Ordered free list (every variable that is not epsilon-binding).  Every warp evaluates all chunks of
+        // 32 variables (a handful of ballots) and writes the slice it owns, so nf is known to every thread
+        // without a broadcast and no warp is held up; very wide problems fall back to warp 0.
+        int nf = 0;
+        const int nchunk = (nv + Ctx::WS - 1) / Ctx::WS;
+        if (nchunk <= cx.nwarp) {
+            for (int ci = 0; ci < nchunk; ++ci) {
+                const int v = ci * Ctx::WS + cx.lane;
                 const bool isf = v < nv && !(!(uint8_t)W.vfree[v] && (T)nu[v] <= epsb && (T)W.g[v] > (T)0);
                 const unsigned m = cx.ballot(isf);
-                if (v < nv) {
-                    const int pos = nfb + cx.lanes_below(m);
+                if (ci == cx.warp && v < nv) {
+                    const int pos = nf + cx.lanes_below(m);
                     W.fpos[v] = isf ? pos : -1;
-                    if (isf) W.flist[pos] = v;
+                    if (isf) W.flist[pos] = v; else W.dir[v] = W.g[v];      // binding set: gradient step
                 }
-                nfb += cx.popc(m);
+                nf += cx.popc(m);
             }
-            if (cx.lane == 0) W.fpos[nv] = nfb;
+            nw_hessian_update(cx, W, rc);      // (ends with a barrier: flist / fpos / dir visible too)
+        } else {
+            if (cx.warp == 0) {
+                int nfb = 0;
+                for (int v0 = 0; v0 < nv; v0 += Ctx::WS) {
+                    const int v = v0 + cx.lane;
+                    const bool isf = v < nv && !(!(uint8_t)W.vfree[v] && (T)nu[v] <= epsb && (T)W.g[v] > (T)0);
+                    const unsigned m = cx.ballot(isf);
+                    if (v < nv) {
+                        const int pos = nfb + cx.lanes_below(m);
+                        W.fpos[v] = isf ? pos : -1;
+                        if (isf) W.flist[pos] = v; else W.dir[v] = W.g[v];
+                    }
+                    nfb += cx.popc(m);
+                }
+                if (cx.lane == 0) W.fpos[nv] = nfb;
+            }
+            nw_hessian_update(cx, W, rc);
+            nf = (int)W.fpos[nv];
         }
-        cx.phase(8);
-        nw_hessian_update(cx, W, rc);          // (ends with a barrier: flist / fpos visible too)
-        const int nf = (int)W.fpos[nv];
-        cx.phase(9);
         // L <- [H_FF + reg I ; g_F^T]
         for (int a = cx.warp; a <= nf; a += cx.nwarp) {
             const HPtr<TH, HOT> la = W.L + tri(a);
@@ -707,24 +722,19 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<TC, HOT>
             }
         }
         cx.sync();
-        cx.phase(10);
         const HPtr<TH, HOT> invd = W.xs + (nv + 2);
         ldlt_blocked<TH, HPtr<TH, HOT> >(cx, W.L, nf, invd, piv_floor);
-        cx.phase(11);
         // back substitution D L^T x = z by warp 0 (column oriented, no reductions, no divisions)
         if (cx.warp == 0) {
             const HPtr<TH, HOT> z = W.L + tri(nf);
             for (int j = nf - 1; j >= 0; --j) {
                 const TH xj = (TH)z[j] * (TH)invd[j];
                 cx.syncwarp();
-                if (cx.lane == 0) W.xs[j] = xj;
+                if (cx.lane == 0) W.dir[(int)W.flist[j]] = (T)xj;
                 for (int i = cx.lane; i < j; i += Ctx::WS) z[i] -= (TH)W.L[tri(j) + i] * xj;
                 cx.syncwarp();
             }
         }
-        cx.sync();
-        cx.phase(12);
-        for (int v = cx.tid; v < nv; v += cx.nthr) { const int fp = W.fpos[v]; W.dir[v] = fp >= 0 ? (T)(TH)W.xs[fp] : (T)W.g[v]; }
         cx.sync();
         // Armijo along the projection arc
         T alpha = (T)1, ft = f;
@@ -752,7 +762,6 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<TC, HOT>
         HPtr<T, HOT> t1 = nu; nu = nut; nut = t1;
         f = ft;
     }
-    cx.phase(13);
     out.r = rc.raw(); out.iters = it; out.status = status;
 }
 
@@ -1011,7 +1020,6 @@ CAVE_DEV bool solve_instance_t(Ctx& cx, const Instance& in, Arena& ar, const TIO
     Result<T> res; res.r = r.raw(); res.iters = 0; res.status = ST_SKIPPED;
     const bool empty = in.nvalid == 0;
     if (!nospace) {
-        cx.phase(0);
         T cc = (T)0;
         for (int k = cx.tid; k < d; k += cx.nthr) { const TIO vc = (TIO)(ep.sign * (double)pred[k]); const T v = (T)vc; c[k] = vc; r[k] = v; cc += v * v; }
         cc = cx.block_sum(cc);
@@ -1044,7 +1052,6 @@ CAVE_DEV bool solve_instance_t(Ctx& cx, const Instance& in, Arena& ar, const TIO
         for (int k = cx.tid; k < d; k += cx.nthr) { grad_out[k] = (TIO)NAN; if (proj_out) proj_out[k] = (TIO)NAN; }
         return true;
     }
-    cx.phase(14);
     epilogue<T, TIO, HPtr<TIO, HOT> >(cx, in, ep, c, res.r, ep.mode != MODE_HEURISTIC, empty, grad_out, proj_out, loss_out, rnorm_out);
     if (cx.tid == 0) { *status_out = res.status; *iters_out = res.iters; }
     return true;

@@ -1,18 +1,19 @@
-// Kernel 1 — scan/pack: ONE streaming pass over A (the HBM-bound part of the path).
+// Kernel 1 — scan/pack: ONE streaming pass over A (the HBM-bound part of the path).  One CTA per instance.
 //
-// One CTA per instance.  Row tiles are brought into a shared-memory ring with 1-D TMA bulk
-// copies (cp.async.bulk ... mbarrier::complete_tx) issued by one thread; eight warps consume:
-//   phase A  warp per row : aligned 128-bit shared loads; a warp-uniform "all four lanes' words
-//                           are zero" test skips the arithmetic for the (dominant) zero words,
-//                           so sparse rows cost ~2 instructions per element.  Per row: non-zero
-//                           count, and for rows that need them sum|a|, sum a^2, two order-free
-//                           64-bit row hashes (for +-row matching in the solver).
-//   phase B  one thread   : ordered bookkeeping of singleton rows (cone types, +-1 average terms)
-//            all threads  : column-parallel accumulation of a/||a|| over the general rows,
-//            warp per row : compaction of each general row into the packed CSR of the instance
-// Everything `_average_ctrs` (src/cave.py:222-228) and the row mask of `_project_nnls`
-// (src/cave.py:303) recompute on the host for every call is produced here in one read of A.
-// All accumulation orders are fixed, so the pack is bit-reproducible run to run.
+// Two variants, chosen by row length (launch_scan):
+//  * scan_rows_kernel (rows up to a few KB — every shipped model): warp-streaming, see its comment below;
+//    measured 5.4 TB/s = 83 % of the measured HBM copy peak at TSP-50 (profiles/r1_ncu_summary.txt).
+//  * scan_kernel (any row length up to the ABI limit): row tiles go through a CTA-wide shared-memory ring fed by
+//    1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) issued by one thread; phase A: one warp per
+//    row, aligned 128-bit shared loads with a warp-uniform all-zero test, per-row non-zero count / sum|a| /
+//    sum a^2; phase B: one thread does the ordered bookkeeping of singleton rows, all threads accumulate
+//    a/||a|| column-parallel over the general rows, one warp per general row compacts it into the packed CSR
+//    and hashes it.
+// Both produce everything `_average_ctrs` (src/cave.py:222-228) and the row mask of `_project_nnls`
+// (src/cave.py:303) recompute on the host for every call, in one read of A, plus what the solver needs: per
+// coordinate singleton cone types, the general-row list with a packed CSR, and two order-free 64-bit row
+// hashes for +-row matching.  Accumulation orders are fixed (or exact integer arithmetic), so the pack is
+// bit-reproducible run to run.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>

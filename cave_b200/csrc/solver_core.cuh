@@ -321,7 +321,7 @@ struct NewtonWork {
     HPtr<uint8_t, HOT> wflag;                     // [d] psi'(r_k) currently folded into H
     HPtr<TH, HOT> H;                              // [nv, nv] lower triangle of B W B^T, kept up to date
     HPtr<TH, HOT> L;                              // [(nf+1), ldl] LDL^T work array with the rhs as last row
-    HPtr<TH, HOT> xs;                             // [nv] Newton step on the free set, then 1/d_j
+    HPtr<TH, HOT> xs;                             // scratch; reciprocal pivots 1/d_j live at xs + nv + 2
 };
 
 template <class VT, class T, class TH, class TC, bool HOT>

@@ -439,19 +439,19 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     W.vfree = ar.geth<HOT, uint8_t>(mB + 1);
     W.wflag = ar.geth<HOT, uint8_t>(d + 1);
     HPtr<uint8_t, HOT> ctype_s = ar.geth<HOT, uint8_t>(d + 1);
-    // cold: setup scratch and sparse structure
     W.rptr = ar.get<int>(mB + 2);
-    // cold, setup only (global slot)
-    int* goff = ar.get_gl<int>(mB + 2);           // row offsets in the source CSR (pack, or the one built here)
-    int* gcnt = ar.get_gl<int>(mB + 2);           // non-zeros per general row
-    W.grow = ar.get_gl<int>(mB + 1);
-    W.rtype = ar.get_gl<uint8_t>(mB + 1);
     W.vrow = ar.get<int>(mB + 1);
-    uint64_t* hpos = ar.get_gl<uint64_t>(mB + 1);
-    uint64_t* hneg = ar.get_gl<uint64_t>(mB + 1);
-    int* cand = ar.get_gl<int>(mB + 1);
-    W.cur = ar.get_gl<int>(d + 1);
+    // cold: sparse structure first (it is read in every iteration), then the setup-only scratch, which takes
+    // whatever shared memory is left and otherwise lives in the global slot
     W.cptr = ar.get<int>(d + 2);
+    int* goff = ar.get<int>(mB + 2);              // row offsets in the source CSR (pack, or the one built here)
+    int* gcnt = ar.get<int>(mB + 2);              // non-zeros per general row
+    W.grow = ar.get<int>(mB + 1);
+    W.rtype = ar.get<uint8_t>(mB + 1);
+    uint64_t* hpos = ar.get<uint64_t>(mB + 1);
+    uint64_t* hneg = ar.get<uint64_t>(mB + 1);
+    int* cand = ar.get<int>(mB + 1);
+    W.cur = ar.get<int>(d + 1);
     if (ar.overflow) return false;
     for (int k = cx.tid; k < d; k += cx.nthr) { ctype_s[k] = in.ctype[k]; W.wflag[k] = 0; }
     W.ctype = ctype_s;

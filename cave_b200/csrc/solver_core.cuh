@@ -669,10 +669,15 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<TC, HOT>
     const HPtr<T, HOT> rc = W.r;       // r is updated in place by every trial evaluation
     T f, dummy = (T)0;
     nw_eval2(cx, W, nu, rc, f, dummy);
-    int status = ST_ITER_CAP, it = 0;
+    int status = ST_ITER_CAP, it = 0, since_best = 0;
+    T res_best = (T)1e300;
     for (; it < max_iter; ++it) {
         const T res = nw_grad(cx, W, rc, W.g, nu);
         if (!(res > tol)) { status = ST_CONVERGED; break; }
+        // stagnation at the floating-point floor: the KKT residual is already tiny and has not halved for five
+        // iterations (it hovers a hair above the tolerance) -> converged, not an iteration-cap failure
+        if (res < (T)0.5 * res_best) { res_best = res; since_best = 0; }
+        else if (++since_best >= 5 && res <= (T)8 * tol) { status = ST_CONVERGED; break; }
         const T epsb = res < (T)1e-3 ? res : (T)1e-3;
         // Ordered free list (every variable that is not epsilon-binding).  Every warp evaluates all chunks of
         // 32 variables (a handful of ballots) and writes the slice it owns, so nf is known to every thread
@@ -738,7 +743,7 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<TC, HOT>
         cx.sync();
         // Armijo along the projection arc
         T alpha = (T)1, ft = f;
-        bool ok = false;
+        bool ok = false, at_floor = false;
         for (int ls = 0; ls < max_ls; ++ls) {
             T dec = (T)0;
             for (int v = cx.tid; v < nv; v += cx.nthr) {
@@ -750,6 +755,9 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<TC, HOT>
             }
             cx.sync();
             nw_eval2(cx, W, nut, rc, ft, dec);
+            // Predicted AND actual change below the rounding level of f: no further progress is representable; the trial
+            // point is as good as the current one (r already belongs to it), so take it and stop.
+            if (ls == 0 && cabs(dec) <= (T)16 * eps_mach<T>() * f && cabs(ft - f) <= (T)16 * eps_mach<T>() * f) { ok = true; at_floor = true; break; }
             if (ft <= f - (T)1e-4 * dec + (T)4 * eps_mach<T>() * f) { ok = true; break; }
             alpha *= (T)0.5;
         }
@@ -761,6 +769,7 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<TC, HOT>
         }
         HPtr<T, HOT> t1 = nu; nu = nut; nut = t1;
         f = ft;
+        if (at_floor) { status = ST_CONVERGED; ++it; break; }
     }
     out.r = rc.raw(); out.iters = it; out.status = status;
 }
@@ -1034,7 +1043,7 @@ CAVE_DEV bool solve_instance_t(Ctx& cx, const Instance& in, Arena& ar, const TIO
                     for (int k = cx.tid; k < d; k += cx.nthr) cd[k] = (T)(TIO)c[k];
                     cx.sync();
                 }
-                lh_solve<T, TH>(cx, in, ar, cd, r.raw(), cnorm, opt, res);
+                lh_solve<T, T>(cx, in, ar, cd, r.raw(), cnorm, opt, res);    // dense path: float64 factor in both modes
             } else {
                 newton_solve<T, TH, TIO, HOT>(cx, in, ar, c, r, cnorm, opt, res);
             }

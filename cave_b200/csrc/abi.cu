@@ -180,7 +180,7 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     sp.max_iter = opts ? opts->max_iter : 0; sp.max_ls = opts ? opts->max_linesearch : 0; sp.tol = opts ? opts->tol : 0.0;
     sp.inst_index = indexed ? opts->inst_index : nullptr;
     int threads = env_int("CAVE_SOLVE_THREADS", 256);
-    if (threads != 128 && threads != 256) threads = 256;
+    if (threads < 32 || threads > 256 || threads % 32) threads = 256;
     ce = cave::launch_solve(sp, compute_dtype == CAVE_F32, io_dtype == CAVE_F32, (int)n_ctas, threads, st);
     if (ce != cudaSuccess) return fail(CAVE_ECUDA, "solve kernel launch failed: %s", cudaGetErrorString(ce));
 

@@ -86,6 +86,17 @@ struct Arena {
     }
 };
 
+// Bump allocator over a borrowed region (an array that is idle during setup); falls back to the arena's cold side.
+struct SubArena {
+    char* base; size_t cap, off;
+    CAVE_DEV void init(char* b, size_t c) { base = b; cap = c & ~(size_t)15; off = 0; }
+    template <class U> CAVE_DEV U* get(Arena& ar, size_t n) {
+        const size_t bytes = (n * sizeof(U) + 15) & ~(size_t)15;
+        if (off + bytes <= cap) { U* p = (U*)(base + off); off += bytes; return p; }
+        return ar.get<U>(n);
+    }
+};
+
 // ctype bit0: a row +a*e_k exists (positive residual absorbed); bit1: a row -a*e_k exists (negative absorbed)
 template <class T> CAVE_DEV bool psi_active(T r, int t) {
     return t == 0 ? true : (r > (T)0 ? !(t & 1) : (r < (T)0 ? !(t & 2) : false));
@@ -320,6 +331,7 @@ struct NewtonWork {
     int* cur;                                     // [d] CSC fill cursors (setup only)
     HPtr<uint8_t, HOT> wflag;                     // [d] psi'(r_k) currently folded into H
     HPtr<TH, HOT> H;                              // [nv, nv] lower triangle of B W B^T, kept up to date
+    HPtr<int, HOT> Hi;                            // ... as exact 32-bit integers when the rows are int8 (i8)
     HPtr<TH, HOT> L;                              // [(nf+1), ldl] LDL^T work array with the rhs as last row
     HPtr<TH, HOT> xs;                             // scratch; reciprocal pivots 1/d_j live at xs + nv + 2
 };
@@ -330,7 +342,17 @@ CAVE_DEV void nw_eval2_t(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, H
     T acc = (T)0;
     for (int k = cx.tid; k < W.d; k += cx.nthr) {
         T rk = (T)(TC)W.c[k];
-        for (int e = W.cptr[k]; e < W.cptr[k + 1]; ++e) rk -= (T)cval[e] * (T)nu[W.crow[e]];
+        int e = W.cptr[k];
+        const int e1 = W.cptr[k + 1];
+        // four gathers in flight per thread (the shared-memory accessors are ordered, so the compiler will
+        // not overlap them by itself); the subtraction order is unchanged
+        for (; e + 4 <= e1; e += 4) {
+            const int i0 = W.crow[e], i1 = W.crow[e + 1], i2 = W.crow[e + 2], i3 = W.crow[e + 3];
+            const T v0 = (T)cval[e], v1 = (T)cval[e + 1], v2 = (T)cval[e + 2], v3 = (T)cval[e + 3];
+            const T n0 = nu[i0], n1 = nu[i1], n2 = nu[i2], n3 = nu[i3];
+            rk -= v0 * n0; rk -= v1 * n1; rk -= v2 * n2; rk -= v3 * n3;
+        }
+        for (; e < e1; ++e) rk -= (T)cval[e] * (T)nu[W.crow[e]];
         rout[k] = rk;
         T q = psi(rk, (int)(uint8_t)W.ctype[k]);
         acc += q * q;
@@ -352,7 +374,16 @@ CAVE_DEV T nw_grad_t(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HOT> 
     for (int v = cx.warp; v < W.nv; v += cx.nwarp) {
         int row = W.vrow[v];
         T acc = (T)0;
-        for (int e = W.rptr[row] + cx.lane; e < W.rptr[row + 1]; e += Ctx::WS) {
+        int e = W.rptr[row] + cx.lane;
+        const int e1 = W.rptr[row + 1];
+        for (; e + 3 * Ctx::WS < e1; e += 4 * Ctx::WS) {       // four gathers in flight per lane, same order
+            const int k0 = W.rcol[e], k1 = W.rcol[e + Ctx::WS], k2 = W.rcol[e + 2 * Ctx::WS], k3 = W.rcol[e + 3 * Ctx::WS];
+            const T v0 = (T)rval[e], v1 = (T)rval[e + Ctx::WS], v2 = (T)rval[e + 2 * Ctx::WS], v3 = (T)rval[e + 3 * Ctx::WS];
+            const T r0 = r[k0], r1 = r[k1], r2 = r[k2], r3 = r[k3];
+            const int t0 = (int)(uint8_t)W.ctype[k0], t1 = (int)(uint8_t)W.ctype[k1], t2 = (int)(uint8_t)W.ctype[k2], t3 = (int)(uint8_t)W.ctype[k3];
+            acc += v0 * psi(r0, t0); acc += v1 * psi(r1, t1); acc += v2 * psi(r2, t2); acc += v3 * psi(r3, t3);
+        }
+        for (; e < e1; e += Ctx::WS) {
             int k = W.rcol[e];
             acc += (T)rval[e] * psi((T)r[k], (int)(uint8_t)W.ctype[k]);
         }
@@ -386,15 +417,28 @@ CAVE_DEV void nw_hessian_update_t(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, 
         const uint8_t now = psi_active((T)r[k], (int)(uint8_t)W.ctype[k]) ? 1 : 0;
         if (now == (uint8_t)W.wflag[k]) continue;
         W.wflag[k] = now;
-        const TH sg = now ? (TH)1 : (TH)-1;
         const int s = W.cptr[k], e = W.cptr[k + 1];
-        for (int e1 = s; e1 < e; ++e1) {
-            const int a = W.crow[e1];
-            const TH va = sg * (TH)cval[e1];
-            for (int e2 = s; e2 <= e1; ++e2) {
-                const int b = W.crow[e2];
-                const int hi = a > b ? a : b, lo = a > b ? b : a;
-                W.H.atomic_add(tri(hi) + lo, va * (TH)cval[e2]);
+        if (sizeof(VT) == 1) {       // int8 rows: H is an exact integer matrix (|H_ij| <= 127^2 d < 2^31)
+            const int sg = now ? 1 : -1;
+            for (int e1 = s; e1 < e; ++e1) {
+                const int a = W.crow[e1];
+                const int va = sg * (int)cval[e1];
+                for (int e2 = s; e2 <= e1; ++e2) {
+                    const int b = W.crow[e2];
+                    const int hi = a > b ? a : b, lo = a > b ? b : a;
+                    W.Hi.atomic_add(tri(hi) + lo, va * (int)cval[e2]);
+                }
+            }
+        } else {
+            const TH sg = now ? (TH)1 : (TH)-1;
+            for (int e1 = s; e1 < e; ++e1) {
+                const int a = W.crow[e1];
+                const TH va = sg * (TH)cval[e1];
+                for (int e2 = s; e2 <= e1; ++e2) {
+                    const int b = W.crow[e2];
+                    const int hi = a > b ? a : b, lo = a > b ? b : a;
+                    W.H.atomic_add(tri(hi) + lo, va * (TH)cval[e2]);
+                }
             }
         }
     }
@@ -444,16 +488,24 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     // cold: sparse structure first (it is read in every iteration), then the setup-only scratch, which takes
     // whatever shared memory is left and otherwise lives in the global slot
     W.cptr = ar.get<int>(d + 2);
-    int* goff = ar.get<int>(mB + 2);              // row offsets in the source CSR (pack, or the one built here)
-    int* gcnt = ar.get<int>(mB + 2);              // non-zeros per general row
-    W.grow = ar.get<int>(mB + 1);
-    W.rtype = ar.get<uint8_t>(mB + 1);
-    uint64_t* hpos = ar.get<uint64_t>(mB + 1);
-    uint64_t* hneg = ar.get<uint64_t>(mB + 1);
-    int* cand = ar.get<int>(mB + 1);
-    W.cur = ar.get<int>(d + 1);
+    // setup-only scratch lives in r (free until the first evaluation writes it) when it fits there
+    SubArena sa; sa.init((char*)W.r.raw(), (size_t)d * sizeof(T));
+    uint64_t* hpos = sa.get<uint64_t>(ar, mB + 1);
+    uint64_t* hneg = sa.get<uint64_t>(ar, mB + 1);
+    int* goff = sa.get<int>(ar, mB + 2);          // row offsets in the source CSR (pack, or the one built here)
+    int* gcnt = sa.get<int>(ar, mB + 2);          // non-zeros per general row
+    W.grow = sa.get<int>(ar, mB + 1);
+    int* cand = sa.get<int>(ar, mB + 1);
+    W.cur = sa.get<int>(ar, d + 1);
+    W.rtype = sa.get<uint8_t>(ar, mB + 1);
     if (ar.overflow) return false;
-    for (int k = cx.tid; k < d; k += cx.nthr) { ctype_s[k] = in.ctype[k]; W.wflag[k] = 0; }
+    for (int k0 = 0; k0 < d; k0 += 8 * cx.nthr) {       // global loads first, then the (ordered) shared stores
+        uint8_t t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int k = k0 + u * cx.nthr + cx.tid; t[u] = k < d ? in.ctype[k] : (uint8_t)0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int k = k0 + u * cx.nthr + cx.tid; if (k < d) { ctype_s[k] = t[u]; W.wflag[k] = 0; } }
+    }
     W.ctype = ctype_s;
     for (int i = cx.tid; i < mB; i += cx.nthr) {
         gen_t g = in.gen[i]; W.grow[i] = g.x; gcnt[i] = g.y; goff[i] = g.z;
@@ -536,8 +588,18 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
 #endif
                 const int pj = goff[jj];
                 bool ok = true;
-                for (int e = cx.lane; e < ni; e += Ctx::WS)
-                    ok = ok && mcol[pi + e] == mcol[pj + e] && mval[pi + e] == -mval[pj + e];
+                for (int e0 = 0; e0 < ni; e0 += 4 * Ctx::WS) {     // all loads of a batch issued before any compare
+                    uint16_t ci[4], cj[4]; float vi[4], vj[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = e0 + u * Ctx::WS + cx.lane;
+                        const bool in_row = e < ni;
+                        ci[u] = in_row ? mcol[pi + e] : (uint16_t)0; cj[u] = in_row ? mcol[pj + e] : (uint16_t)0;
+                        vi[u] = in_row ? mval[pi + e] : 0.f; vj[u] = in_row ? mval[pj + e] : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) ok = ok & (ci[u] == cj[u]) & (vi[u] == -vj[u]);
+                }
                 const unsigned bad = cx.ballot(!ok);
                 if (!bad) c0 = jj;
                 m &= m - 1;
@@ -575,11 +637,13 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     const int nnzc = W.flist[1];
     cx.sync();
     const int nv = W.nv;
-    W.H = ar.geth<HOT, TH>((size_t)tri(nv) + 1);                 // row-packed lower triangles
+    // Integer-valued rows (every shipped model) are kept as int8, and their Hessian as exact int32.
+    W.i8 = (in.csr_ok & 3) == 3;
+    if (W.i8) W.Hi = ar.geth<HOT, int>((size_t)tri(nv) + 1);      // row-packed lower triangles
+    else W.H = ar.geth<HOT, TH>((size_t)tri(nv) + 1);
     W.L = ar.geth<HOT, TH>((size_t)tri(nv + 2) + 1);
     // the CSC feeds eval (several times per iteration) and the Hessian update, the CSR only the gradient:
-    // the CSC gets shared memory first.  Integer-valued rows (every shipped model) are kept as int8.
-    W.i8 = (in.csr_ok & 3) == 3;
+    // the CSC gets shared memory first.
     W.crow = ar.get<uint16_t>(nnzc + 1);
     if (W.i8) W.cval = ar.get<int8_t>(nnzc + 1); else W.cval = ar.get<float>(nnzc + 1);
     if (in.csr_ok) {
@@ -596,8 +660,22 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
         cx.sync();
         for (int v = cx.warp; v < nv; v += cx.nwarp) {
             const int src = goff[W.vrow[v]], dst = W.rptr[v], n = W.rptr[v + 1] - dst;
-            if (W.i8) for (int e = cx.lane; e < n; e += Ctx::WS) { W.rcol[dst + e] = in.pcol[src + e]; ((int8_t*)W.rval)[dst + e] = (int8_t)in.pval[src + e]; }
-            else for (int e = cx.lane; e < n; e += Ctx::WS) { W.rcol[dst + e] = in.pcol[src + e]; ((float*)W.rval)[dst + e] = in.pval[src + e]; }
+            for (int e0 = 0; e0 < n; e0 += 8 * Ctx::WS) {       // eight loads per lane in flight
+                uint16_t cc[8]; float vv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = e0 + u * Ctx::WS + cx.lane;
+                    cc[u] = e < n ? in.pcol[src + e] : (uint16_t)0; vv[u] = e < n ? in.pval[src + e] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = e0 + u * Ctx::WS + cx.lane;
+                    if (e < n) {
+                        W.rcol[dst + e] = cc[u];
+                        if (W.i8) ((int8_t*)W.rval)[dst + e] = (int8_t)vv[u]; else ((float*)W.rval)[dst + e] = vv[u];
+                    }
+                }
+            }
         }
         cx.sync();
         for (int v = cx.tid; v < nv; v += cx.nthr) W.vrow[v] = v;
@@ -607,7 +685,8 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     }
     // CSC: count, scan, fill with a cursor, then order every column by variable id
     for (int k = cx.tid; k <= d; k += cx.nthr) W.cptr[k] = 0;
-    for (uint32_t t = cx.tid; t < tri(nv); t += cx.nthr) W.H[t] = (TH)0;
+    if (W.i8) for (uint32_t t = cx.tid; t < tri(nv); t += cx.nthr) W.Hi[t] = 0;
+    else for (uint32_t t = cx.tid; t < tri(nv); t += cx.nthr) W.H[t] = (TH)0;
     cx.sync();
     for (int v = cx.warp; v < nv; v += cx.nwarp) {
         int row = W.vrow[v];
@@ -721,8 +800,11 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<TC, HOT>
             const HPtr<TH, HOT> la = W.L + tri(a);
             if (a == nf) {
                 for (int b = cx.lane; b < nf; b += Ctx::WS) la[b] = (TH)(T)W.g[(int)W.flist[b]];
+            } else if (W.i8) {
+                const HPtr<int, HOT> ha = W.Hi + tri((int)W.flist[a]);          // flist ascending => flist[a] >= flist[b]
+                for (int b = cx.lane; b <= a; b += Ctx::WS) la[b] = (TH)(int)ha[(int)W.flist[b]] + (a == b ? reg : (TH)0);
             } else {
-                const HPtr<TH, HOT> ha = W.H + tri((int)W.flist[a]);            // flist ascending => flist[a] >= flist[b]
+                const HPtr<TH, HOT> ha = W.H + tri((int)W.flist[a]);
                 for (int b = cx.lane; b <= a; b += Ctx::WS) la[b] = (TH)ha[(int)W.flist[b]] + (a == b ? reg : (TH)0);
             }
         }
@@ -972,12 +1054,23 @@ CAVE_DEV void epilogue(Ctx& cx, const Instance& in, const EpiParams& ep, PC c, c
                        bool have_proj, bool empty_cone,
                        TIO* grad_out, TIO* proj_out, double* loss_out, double* rnorm_out) {
     const int d = in.d;
+    constexpr int U = 8;        // global loads (ctype, avg) of U strides are issued together, ahead of the ordered shared loads
+    const bool use_q = have_proj && !empty_cone;
     double pp = 0.0, qq = 0.0, cc = 0.0;
-    for (int k = cx.tid; k < d; k += cx.nthr) {
-        double ck = (double)c[k];
-        double q = (have_proj && !empty_cone) ? (double)psi(r[k], (int)in.ctype[k]) : 0.0;
-        double p = ck - q;
-        pp += p * p; qq += q * q; cc += ck * ck;
+    for (int k0 = 0; k0 < d; k0 += U * cx.nthr) {
+        int ty[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int k = k0 + u * cx.nthr + cx.tid; ty[u] = (use_q && k < d) ? (int)in.ctype[k] : 0; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = k0 + u * cx.nthr + cx.tid;
+            if (k < d) {
+                const double ck = (double)c[k];
+                const double q = use_q ? (double)psi(r[k], ty[u]) : 0.0;
+                const double p = ck - q;
+                pp += p * p; qq += q * q; cc += ck * ck;
+            }
+        }
     }
     pp = cx.block_sum(pp); qq = cx.block_sum(qq); cc = cx.block_sum(cc);
     const double rnorm = sqrt(qq), pnorm = sqrt(pp), cnorm = sqrt(cc);
@@ -985,20 +1078,34 @@ CAVE_DEV void epilogue(Ctx& cx, const Instance& in, const EpiParams& ep, PC c, c
     const double cden = cnorm > 1e-8 ? cnorm : 1e-8;
     const double rr = ep.inner_ratio;
     const bool push = ep.mode == MODE_INNER && !(rnorm < 1e-7);
+    const bool heur = ep.mode == MODE_HEURISTIC;
+    const bool need_avg = heur || push;
     // target t_k (recomputed in the last pass instead of being stored: no d-vector of scratch)
-    auto target = [&](int k, double ck) -> double {
-        if (ep.mode == MODE_HEURISTIC) return (1.0 - rr) * (ck / cden) + rr * (double)in.avg[k];
-        const double q = empty_cone ? 0.0 : (double)psi(r[k], (int)in.ctype[k]);
+    auto target = [&](int k, double ck, int ty, double av) -> double {
+        if (heur) return (1.0 - rr) * (ck / cden) + rr * av;
+        const double q = empty_cone ? 0.0 : (double)psi(r[k], ty);
         const double ph = (ck - q) / pden;
-        return push ? (1.0 - rr) * ph + rr * (double)in.avg[k] : ph;
+        return push ? (1.0 - rr) * ph + rr * av : ph;
     };
     double tt = 0.0, ct = 0.0;
-    for (int k = cx.tid; k < d; k += cx.nthr) {
-        const double ck = (double)c[k];
-        const double t = target(k, ck);
-        if (proj_out && ep.mode != MODE_HEURISTIC)
-            proj_out[k] = (TIO)(ck - (empty_cone ? 0.0 : (double)psi(r[k], (int)in.ctype[k])));
-        tt += t * t; ct += ck * t;
+    for (int k0 = 0; k0 < d; k0 += U * cx.nthr) {
+        int ty[U]; float av[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = k0 + u * cx.nthr + cx.tid;
+            ty[u] = (!heur && !empty_cone && k < d) ? (int)in.ctype[k] : 0;
+            av[u] = (need_avg && k < d) ? in.avg[k] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = k0 + u * cx.nthr + cx.tid;
+            if (k < d) {
+                const double ck = (double)c[k];
+                const double t = target(k, ck, ty[u], (double)av[u]);
+                if (proj_out && !heur) proj_out[k] = (TIO)(ck - (empty_cone ? 0.0 : (double)psi(r[k], ty[u])));
+                tt += t * t; ct += ck * t;
+            }
+        }
     }
     tt = cx.block_sum(tt); ct = cx.block_sum(ct);
     const double tnorm = sqrt(tt);
@@ -1006,11 +1113,24 @@ CAVE_DEV void epilogue(Ctx& cx, const Instance& in, const EpiParams& ep, PC c, c
     const double cosv = ct / (cden * tden);
     const double invc = cnorm > 0.0 ? 1.0 / cnorm : 0.0;
     const double gs = ep.gscale * ep.sign;
-    for (int k = cx.tid; k < d; k += cx.nthr) {
-        const double ck = (double)c[k];
-        const double v = target(k, ck) / tden;
-        const double w = ck * invc;
-        grad_out[k] = (TIO)(gs * (-(v - cosv * w) / cden));
+    for (int k0 = 0; k0 < d; k0 += U * cx.nthr) {
+        int ty[U]; float av[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = k0 + u * cx.nthr + cx.tid;
+            ty[u] = (!heur && !empty_cone && k < d) ? (int)in.ctype[k] : 0;
+            av[u] = (need_avg && k < d) ? in.avg[k] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = k0 + u * cx.nthr + cx.tid;
+            if (k < d) {
+                const double ck = (double)c[k];
+                const double v = target(k, ck, ty[u], (double)av[u]) / tden;
+                const double w = ck * invc;
+                grad_out[k] = (TIO)(gs * (-(v - cosv * w) / cden));
+            }
+        }
     }
     if (cx.tid == 0) { *loss_out = 1.0 - cosv; *rnorm_out = (ep.mode == MODE_HEURISTIC) ? 0.0 : rnorm; }
 }
@@ -1030,7 +1150,16 @@ CAVE_DEV bool solve_instance_t(Ctx& cx, const Instance& in, Arena& ar, const TIO
     const bool empty = in.nvalid == 0;
     if (!nospace) {
         T cc = (T)0;
-        for (int k = cx.tid; k < d; k += cx.nthr) { const TIO vc = (TIO)(ep.sign * (double)pred[k]); const T v = (T)vc; c[k] = vc; r[k] = v; cc += v * v; }
+        for (int k0 = 0; k0 < d; k0 += 8 * cx.nthr) {       // global loads first, then the (ordered) shared stores
+            TIO pv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int k = k0 + u * cx.nthr + cx.tid; pv[u] = k < d ? pred[k] : (TIO)0; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = k0 + u * cx.nthr + cx.tid;
+                if (k < d) { const TIO vc = (TIO)(ep.sign * (double)pv[u]); const T v = (T)vc; c[k] = vc; r[k] = v; cc += v * v; }
+            }
+        }
         cc = cx.block_sum(cc);
         const T cnorm = (T)sqrt((double)cc);
         const bool finite_in = cc < (T)1e300;              // false for NaN / Inf predictions

@@ -332,6 +332,7 @@ def run_ours(args):
                                 "index per step; host pred_cost in, host loss and gradient out"}
         del A_host
 
+    plan_info = pack.launch_plan(args.precision)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -339,8 +340,8 @@ def run_ours(args):
         "config": {"workload": f"{args.workload} DFJ synthetic (SURVEY App. B), CaVE+ inner_ratio {ratio}, batch {B}/GPU, "
                                f"pred regime {args.regime}, dense float32 [B,{m_max},{d}] resident in HBM, cold pack",
                    "batch_per_gpu": B, "m_max": m_max, "d": d, "l2_policy": "inputs larger than L2 (A = %.1f GB)" % (scan_bytes / 1e9)},
-        "clocks": clocks, "e2e": e2e, "e2e_resident_dataset": e2e_resident, "gpu_launches": 3 * args.steps,
-        "roofline": roofline, "kernels": kernels,
+        "clocks": clocks, "e2e": e2e, "e2e_resident_dataset": e2e_resident, "gpu_launches": 7 * args.steps,
+        "roofline": roofline, "kernels": kernels, "solve_launch_plan": plan_info,
         "solver": {"status_counts": {str(k): int(v) for k, v in zip(*np.unique(status, return_counts=True))},
                    "iters_mean": float(iters.mean()), "iters_max": int(iters.max()), "loss": loss_val},
     }

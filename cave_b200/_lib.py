@@ -15,7 +15,7 @@ F32, F64 = 0, 1
 ST_CONVERGED, ST_ITER_CAP, ST_STALLED, ST_NOSPACE, ST_SKIPPED, ST_BADINPUT, ST_PATH_LH = 0, 1, 2, 3, 4, 5, 0x100
 
 EXPORTS = ("cave_abi_version", "cave_last_error", "cave_get_limits", "cave_pack_bytes",
-           "cave_scratch_bytes", "cave_pack", "cave_forward_backward")
+           "cave_scratch_bytes", "cave_pack", "cave_forward_backward", "cave_plan_offset", "cave_plan_choice")
 
 
 class SolverOpts(ctypes.Structure):
@@ -56,7 +56,11 @@ def load() -> ctypes.CDLL:
     lib.cave_forward_backward.argtypes = [P, P, P, I64, I64, I64, F, I32, F, I32, I32, I32,
                                           ctypes.POINTER(SolverOpts), P, P, P, P, P, P, P,
                                           P, ctypes.c_size_t, P, ctypes.c_size_t, P]
-    for name in ("cave_get_limits", "cave_pack_bytes", "cave_scratch_bytes", "cave_pack", "cave_forward_backward"):
+    lib.cave_plan_offset.argtypes = [I64, I64, I64, SZP]
+    IP = ctypes.POINTER(ctypes.c_int)
+    lib.cave_plan_choice.argtypes = [ctypes.POINTER(ctypes.c_uint64), I64, I32, I32, IP, IP, IP]
+    for name in ("cave_get_limits", "cave_pack_bytes", "cave_scratch_bytes", "cave_pack", "cave_forward_backward",
+                 "cave_plan_offset", "cave_plan_choice"):
         getattr(lib, name).restype = I32
     _lib = lib
     return lib

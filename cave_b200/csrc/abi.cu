@@ -48,8 +48,17 @@ int sm_count() {
     return 148;                     // B200; used only for sizing when no device is visible
 }
 
-int64_t solver_ctas(int64_t B) {
-    int64_t n = (int64_t)sm_count() * env_int("CAVE_SOLVE_CTAS_PER_SM", 2);
+bool solve_forced() {     // experiments: a single launch with explicit thread / CTA / shared-memory settings
+    return getenv("CAVE_SOLVE_THREADS") || getenv("CAVE_SOLVE_CTAS_PER_SM") || getenv("CAVE_SOLVE_SMEM");
+}
+
+// Scratch slots (one per resident CTA of the widest-grid configuration that may run), bounded so that the
+// worst-case slots of a large shape do not take more than 16 GiB; the two-CTAs-per-SM grid is always served.
+int64_t solver_slots(int64_t B, size_t slot_bytes) {
+    const int64_t sms = sm_count();
+    int64_t n = sms * (solve_forced() ? env_int("CAVE_SOLVE_CTAS_PER_SM", 2) : cave::solve_config(0).ctas_per_sm);
+    const int64_t cap = (int64_t)(((size_t)16 << 30) / (slot_bytes ? slot_bytes : 1));
+    if (!solve_forced() && n > cap) n = cap > 2 * sms ? cap : 2 * sms;
     return B < n ? B : n;
 }
 
@@ -91,13 +100,33 @@ int cave_pack_bytes(int64_t B, int64_t m_max, int64_t d, size_t* out) {
     return CAVE_OK;
 }
 
+int cave_plan_offset(int64_t B, int64_t m_max, int64_t d, size_t* out) {
+    if (!out) return fail(CAVE_EINVAL, "out is null");
+    if (int e = check_shape(B, m_max, d)) return e;
+    *out = cave::make_pack_layout(B, m_max, d).plan;
+    return CAVE_OK;
+}
+
+int cave_plan_choice(const uint64_t* plan_host, int64_t d, int io_dtype, int compute_dtype,
+                     int* threads, int* ctas_per_sm, int* smem_bytes) {
+    if (!plan_host) return fail(CAVE_EINVAL, "plan_host is null");
+    unsigned long long pl[8];
+    for (int i = 0; i < 8; ++i) pl[i] = plan_host[i];
+    const int c = cave::choose_solve_config(pl, compute_dtype == CAVE_F32 ? 4 : 8, io_dtype == CAVE_F64 ? (size_t)d * 4 : 0);
+    const cave::SolveConfig cfg = cave::solve_config(c);
+    if (threads) *threads = cfg.threads;
+    if (ctas_per_sm) *ctas_per_sm = cfg.ctas_per_sm;
+    if (smem_bytes) *smem_bytes = cfg.smem_bytes;
+    return c;
+}
+
 int cave_scratch_bytes(int64_t B, int64_t m_max, int64_t d, int compute_dtype, const cave_solver_opts* opts, size_t* out) {
     if (!out) return fail(CAVE_EINVAL, "out is null");
     if (int e = check_shape(B, m_max, d)) return e;
     if (compute_dtype != CAVE_F32 && compute_dtype != CAVE_F64) return fail(CAVE_EINVAL, "bad compute_dtype %d", compute_dtype);
     int64_t cr, cz;
     resolve_caps(opts, m_max, d, &cr, &cz);
-    *out = cave::make_scratch_layout(B, d, cr, cz, 8, solver_ctas(B)).total;
+    *out = cave::make_scratch_layout(B, d, cr, cz, 8, solver_slots(B, cave::solver_slot_bytes(d, cr, cz, 8))).total;
     return CAVE_OK;
 }
 
@@ -117,8 +146,17 @@ int cave_pack(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, i
     p.gen4 = (int4*)(base + L.gen); p.ctype = (unsigned char*)(base + L.ctype); p.avg = (float*)(base + L.avg);
     p.ghash = (ulonglong2*)(base + L.ghash); p.csr_col = (uint16_t*)(base + L.csr_col); p.csr_val = (float*)(base + L.csr_val);
     p.cap_nnz = (int)L.cap_nnz; p.csr_ok = (int*)(base + L.csrok); p.maxl1 = (float*)(base + L.maxl1); p.maxl2 = (float*)(base + L.maxl2);
-    cudaError_t e = cave::launch_scan(p, (cudaStream_t)stream);
+    cudaError_t e = cudaMemsetAsync(base + L.plan, 0, 64, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(CAVE_ECUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+    e = cave::launch_scan(p, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(CAVE_ECUDA, "scan kernel launch failed: %s", cudaGetErrorString(e));
+    cave::PlanParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.B = (int)B; pp.m_max = (int)m_max; pp.d = (int)d;
+    pp.nvalid = p.nvalid; pp.ngen = p.ngen; pp.gennnz = p.gennnz; pp.nsingc = p.nsingc; pp.csr_ok = p.csr_ok;
+    pp.gen4 = p.gen4; pp.ghash = p.ghash; pp.plan = (unsigned long long*)(base + L.plan);
+    e = cave::launch_plan(pp, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(CAVE_ECUDA, "plan kernel launch failed: %s", cudaGetErrorString(e));
     return CAVE_OK;
 }
 
@@ -148,8 +186,8 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     int64_t cr, cz;
     resolve_caps(opts, m_max, d, &cr, &cz);
     const size_t T = 8;   // state vectors are double in both modes; sized for the f64 factor
-    const int64_t n_ctas = solver_ctas(B);
-    const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, cr, cz, T, n_ctas);
+    const int64_t n_slots = solver_slots(B, cave::solver_slot_bytes(d, cr, cz, T));
+    const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, cr, cz, T, n_slots);
     if (scratch_bytes < SL.total) return fail(CAVE_ENOSPC, "scratch buffer has %zu bytes, %zu needed", scratch_bytes, SL.total);
 
     cudaStream_t st = (cudaStream_t)stream;
@@ -174,15 +212,33 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     sp.counter = (int*)(sb + SL.counter); sp.loss64 = (double*)(sb + SL.loss64); sp.rnorm64 = (double*)(sb + SL.rnorm64);
     sp.status = (int*)(sb + SL.status); sp.iters = (int*)(sb + SL.iters);
     sp.slots = sb + SL.slots; sp.slot_bytes = SL.slot_bytes;
-    sp.smem_bytes = env_int("CAVE_SOLVE_SMEM", 110 * 1024);   // two CTAs per SM
     sp.mode = mode; sp.inner_ratio = inner_ratio; sp.sign = sign;
     sp.gscale = reduction == CAVE_REDUCE_MEAN ? 1.0 / (double)B : 1.0;
     sp.max_iter = opts ? opts->max_iter : 0; sp.max_ls = opts ? opts->max_linesearch : 0; sp.tol = opts ? opts->tol : 0.0;
     sp.inst_index = indexed ? opts->inst_index : nullptr;
-    int threads = env_int("CAVE_SOLVE_THREADS", 256);
-    if (threads < 32 || threads > 256 || threads % 32) threads = 256;
-    ce = cave::launch_solve(sp, compute_dtype == CAVE_F32, io_dtype == CAVE_F32, (int)n_ctas, threads, st);
-    if (ce != cudaSuccess) return fail(CAVE_ECUDA, "solve kernel launch failed: %s", cudaGetErrorString(ce));
+    sp.plan = (const unsigned long long*)(pb + PL.plan);
+    if (solve_forced()) {
+        sp.smem_bytes = env_int("CAVE_SOLVE_SMEM", 110 * 1024);
+        int threads = env_int("CAVE_SOLVE_THREADS", 256);
+        if (threads < 32 || threads > 256 || threads % 32) threads = 256;
+        sp.cfg_id = -1;
+        ce = cave::launch_solve(sp, compute_dtype == CAVE_F32, io_dtype == CAVE_F32, (int)n_slots, threads, st);
+        if (ce != cudaSuccess) return fail(CAVE_ECUDA, "solve kernel launch failed: %s", cudaGetErrorString(ce));
+    } else {
+        // every candidate configuration is enqueued; the pack's plan statistics select exactly one on the device
+        // and the others return immediately (no host round trip, a few microseconds of launch overhead)
+        const int only = env_int("CAVE_SOLVE_CFG", -1);
+        for (int i = 0; i < cave::kNumSolveConfigs; ++i) {
+            const cave::SolveConfig cfg = cave::solve_config(i);
+            if (only >= 0 && only < cave::kNumSolveConfigs && i != only) continue;
+            int64_t grid = (int64_t)sm_count() * cfg.ctas_per_sm;
+            if (grid > n_slots) grid = n_slots;
+            sp.smem_bytes = cfg.smem_bytes;
+            sp.cfg_id = (only >= 0 && only < cave::kNumSolveConfigs) ? -1 : i;
+            ce = cave::launch_solve(sp, compute_dtype == CAVE_F32, io_dtype == CAVE_F32, (int)grid, cfg.threads, st);
+            if (ce != cudaSuccess) return fail(CAVE_ECUDA, "solve kernel launch failed: %s", cudaGetErrorString(ce));
+        }
+    }
 
     cave::FinalizeParams fp;
     memset(&fp, 0, sizeof(fp));

@@ -26,8 +26,10 @@ CAVE_HD size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 //   csrok[B], maxl1[B], maxl2[B]   packed-CSR complete flag; max ||a||_1, max ||a||_2^2 over general rows
 //   ghash[B, m_max]   indexed by ROW: order-free 64-bit hashes of the row and of its negation (general rows only)
 //   csr_col/val[B, cap_nnz]   the general rows' non-zeros, row after row, columns ascending
+//   plan[8]     uint64 batch statistics written by the plan kernel (see PlanStats): the solve kernel's
+//               launch configuration is chosen from them on the device, without a host round trip
 struct PackLayout {
-    size_t nvalid, navg, ngen, gennnz, nsingc, gen, ctype, avg, csrok, maxl1, maxl2, ghash, csr_col, csr_val, total;
+    size_t nvalid, navg, ngen, gennnz, nsingc, gen, ctype, avg, csrok, maxl1, maxl2, ghash, csr_col, csr_val, plan, total;
     int64_t dpad, cap_nnz;
 };
 
@@ -57,8 +59,56 @@ CAVE_HD PackLayout make_pack_layout(int64_t B, int64_t m_max, int64_t d) {
     L.ghash = o;  o = align_up(o + (size_t)B * (size_t)m_max * 16, 256);
     L.csr_col = o; o = align_up(o + (size_t)B * (size_t)L.cap_nnz * 2, 256);
     L.csr_val = o; o = align_up(o + (size_t)B * (size_t)L.cap_nnz * 4, 256);
+    L.plan = o;   o = align_up(o + 64, 256);
     L.total = o;
     return L;
+}
+
+// ---- launch plan of the solve kernel
+// The solver is latency bound, so small instances want many small CTAs per SM and large ones few big CTAs.
+// Which one applies depends on the data (general rows, +- pairs, non-zeros), which only the device knows
+// after the scan; the plan kernel therefore reduces per-instance shared-memory footprints into PlanStats and
+// every candidate configuration is launched — the ones the statistics do not select exit at once.
+enum { PLAN_N = 0, PLAN_SUM8 = 1, PLAN_SUM4 = 2, PLAN_MAXHOT8 = 3, PLAN_MAXHOT4 = 4 };   // indices into plan[]
+struct SolveConfig { int threads, ctas_per_sm, smem_bytes; };
+constexpr int kNumSolveConfigs = 4;
+CAVE_HD SolveConfig solve_config(int i) {
+    // 4 x 128 x 128 registers fills the register file; shared memory per CTA leaves room for the static part
+    const SolveConfig t[kNumSolveConfigs] = {{64, 8, 28160}, {128, 4, 56320}, {160, 3, 75776}, {256, 2, 112640}};
+    return t[i];
+}
+CAVE_HD size_t a16(size_t v) { return (v + 15) & ~(size_t)15; }
+// Shared-memory footprint of one instance (bytes), mirroring the Arena requests of solver_core.cuh.
+//   hot  : arrays that must be in shared memory for the fast layout
+//   work : hot + the CSC and the pointer arrays + half of the CSR (which may spill to the global slot at little cost)
+CAVE_HD void instance_footprint(int64_t d, int64_t ngen, int64_t nv, int64_t nnz_kept, bool i8, bool dense_path,
+                                size_t th, size_t* hot, size_t* work) {
+    const size_t D = (size_t)d, M = (size_t)ngen, V = (size_t)nv, Z = (size_t)nnz_kept;
+    size_t h = a16(D * 4) + a16(D * 8);                             // c (I/O dtype, 4 assumed here) and r
+    if (ngen == 0) { *hot = h; *work = h; return; }
+    if (dense_path) {                                               // Lawson-Hanson: Gram + factor, three d-vectors
+        const size_t k = (M < D ? M : D) + 1;
+        size_t w = h + 2 * a16(D * 8) + 2 * a16(k * k * 8) + 8 * a16(k * 8) + a16(M * 5);
+        *hot = h; *work = w; return;
+    }
+    h += 4 * a16((M + 1) * 8) + a16((2 * M + 6) * th) + 256 + 2 * a16((M + 2) * 4) + a16(M + 1) + 2 * a16(D + 1);
+    h += a16((V * (V + 1) / 2 + 1) * (i8 ? 4 : th)) + a16(((V + 2) * (V + 3) / 2 + 1) * th);
+    size_t w = h + a16((M + 2) * 4) + a16((M + 1) * 4) + a16((D + 2) * 4) + a16((Z + 1) * 2) + a16((Z + 1) * (i8 ? 1 : 4));
+    w += (a16((Z + 8) * 2) + a16((Z + 4) * (i8 ? 1 : 4))) / 2;        // half of the CSR: spilling it costs little, not nothing
+    *hot = h; *work = w;
+}
+// Smallest configuration whose shared memory holds the average working set with 5 % to spare and the largest
+// hot set outright; the widest one otherwise.  io_extra: bytes added when c is stored in float64.
+CAVE_HD int choose_solve_config(const unsigned long long* plan, size_t th, size_t io_extra) {
+    const unsigned long long n = plan[PLAN_N];
+    if (n == 0) return kNumSolveConfigs - 1;
+    const size_t avg = (size_t)((th == 8 ? plan[PLAN_SUM8] : plan[PLAN_SUM4]) / n) + io_extra;
+    const size_t mx = (size_t)(th == 8 ? plan[PLAN_MAXHOT8] : plan[PLAN_MAXHOT4]) + io_extra;
+    for (int i = 0; i < kNumSolveConfigs - 1; ++i) {
+        const size_t cap = (size_t)solve_config(i).smem_bytes;
+        if (avg * 20 <= cap * 19 && mx + 1024 <= cap) return i;
+    }
+    return kNumSolveConfigs - 1;
 }
 
 // Solver scratch: [work counter][loss64 B][rnorm64 B][status B][iters B][one slot per CTA]
@@ -71,7 +121,7 @@ CAVE_HD size_t solver_slot_bytes(int64_t d, int64_t cap_rows, int64_t cap_nnz, s
     const size_t r = (size_t)cap_rows + 2, dd = (size_t)d + 2;
     // Newton path (upper bound over every Arena::get in nw_setup / newton_solve)
     size_t nw = 3 * dd * T + 4 * dd + 4 * dd + r * (6 * T + 4 + 4 + 1 + 4 + 1 + 4 + 4 + 8 + 4)
-              + (size_t)(cap_nnz + 2) * 12 + r * r * T + (r + 1) * (r + 2) * T;
+              + (size_t)(cap_nnz + 2) * 12 + (r * (r + 1) / 2 + (r + 2) * (r + 3) / 2 + 8) * T;
     // Lawson-Hanson path
     const size_t k = (cap_rows < d ? (size_t)cap_rows : (size_t)d) + 2;
     size_t lh = 3 * dd * T + dd * T + k * (5 * T + 8) + r * 5 + 2 * k * k * T;

@@ -602,4 +602,59 @@ cudaError_t launch_scan(const ScanParams& p0, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// ---- plan kernel: one warp per instance estimates the solver's shared-memory footprint (general rows, rows
+// that will merge into +- pairs by hash, non-zeros kept) and reduces it into the batch statistics from which
+// the solve kernel's launch configuration is chosen on the device (layout.cuh).  Integer sums and maxima:
+// order independent, hence reproducible.
+constexpr int kPlanMaxRows = 512;       // hashes staged per warp; beyond that the pair estimate is skipped
+__global__ void __launch_bounds__(256) plan_kernel(PlanParams p) {
+    __shared__ unsigned long long hp[8][kPlanMaxRows];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.x * 8 + w;
+    if (b >= p.B) return;
+    const int ngen = p.ngen[b], nnz = p.gennnz[b], ok = p.csr_ok[b];
+    const bool dense_path = p.nsingc[b] == 0;
+    int paired = 0;
+    if (ngen > 0 && !dense_path && (ok & 1) && ngen <= kPlanMaxRows) {
+        const int4* gen = p.gen4 + (size_t)b * p.m_max;
+        const ulonglong2* gh = p.ghash + (size_t)b * p.m_max;
+        unsigned long long want[kPlanMaxRows / 32];
+#pragma unroll
+        for (int u = 0; u < kPlanMaxRows / 32; ++u) {
+            const int i = u * 32 + lane;
+            want[u] = 0;
+            if (i < ngen) { const ulonglong2 h = gh[gen[i].x]; hp[w][i] = h.x; want[u] = h.y; }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < kPlanMaxRows / 32; ++u) {
+            const int i = u * 32 + lane;
+            if (u * 32 < ngen) {
+                bool hit = false;
+                for (int j = 0; j < ngen; ++j) hit |= (j != i) & (hp[w][j] == want[u]);
+                paired += (i < ngen && hit) ? 1 : 0;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) paired += __shfl_xor_sync(0xffffffffu, paired, o);
+    }
+    if (lane == 0) {
+        const int nv = ngen - paired / 2;
+        const long long nnz_kept = ngen > 0 ? (long long)nnz * nv / ngen : 0;
+        const bool skip = p.nvalid[b] == 0;
+        size_t hot8, work8, hot4, work4;
+        instance_footprint(p.d, skip ? 0 : ngen, nv, nnz_kept, (ok & 3) == 3, dense_path, 8, &hot8, &work8);
+        instance_footprint(p.d, skip ? 0 : ngen, nv, nnz_kept, (ok & 3) == 3, dense_path, 4, &hot4, &work4);
+        atomicAdd(p.plan + PLAN_N, 1ull);
+        atomicAdd(p.plan + PLAN_SUM8, (unsigned long long)work8);
+        atomicAdd(p.plan + PLAN_SUM4, (unsigned long long)work4);
+        atomicMax(p.plan + PLAN_MAXHOT8, (unsigned long long)hot8);
+        atomicMax(p.plan + PLAN_MAXHOT4, (unsigned long long)hot4);
+    }
+}
+
+cudaError_t launch_plan(const PlanParams& p, cudaStream_t stream) {
+    plan_kernel<<<dim3((unsigned)((p.B + 7) / 8)), dim3(256), 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
 }  // namespace cave

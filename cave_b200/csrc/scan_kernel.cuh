@@ -26,4 +26,13 @@ struct ScanParams {
 
 cudaError_t launch_scan(const ScanParams& p, cudaStream_t stream);
 
+struct PlanParams {
+    int B, m_max, d;
+    const int *nvalid, *ngen, *gennnz, *nsingc, *csr_ok;
+    const int4* gen4;
+    const ulonglong2* ghash;
+    unsigned long long* plan;   // zeroed by the caller on the same stream
+};
+cudaError_t launch_plan(const PlanParams& p, cudaStream_t stream);
+
 }  // namespace cave

@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256, 2) solve_kernel(SolveParams p) {
     extern __shared__ __align__(16) char smem[];
     __shared__ double red[64];
     __shared__ int s_b;
+    if (p.cfg_id >= 0 && choose_solve_config(p.plan, sizeof(T), sizeof(TIO) == 8 ? (size_t)p.d * 4 : 0) != p.cfg_id) return;
     Ctx cx(red);
     char* slot = p.slots + (size_t)blockIdx.x * p.slot_bytes;
     EpiParams ep; ep.mode = p.mode; ep.inner_ratio = p.inner_ratio; ep.sign = p.sign; ep.gscale = p.gscale;

@@ -35,6 +35,10 @@ struct SolveParams {
     int max_iter, max_ls;
     double tol;
     const int* inst_index; // nullable: batch position -> instance of the (dataset-wide) pack and of A
+    // launch plan: this launch is configuration cfg_id of layout.cuh's table and runs only if the pack's plan
+    // statistics select it (cfg_id < 0: forced, no check)
+    int cfg_id;
+    const unsigned long long* plan;
 };
 
 struct FinalizeParams {

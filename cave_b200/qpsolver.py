@@ -70,6 +70,22 @@ class CavePack:
     data_ptr: int
     ctrs: torch.Tensor | None = None
 
+    def launch_plan(self, precision: str = "fp64", io_dtype: torch.dtype = torch.float32) -> dict:
+        """Diagnostics (synchronises): the solve-kernel configuration the pack's statistics select on the device."""
+        lib = _lib.load()
+        B, m, d = self.shape
+        off = ctypes.c_size_t()
+        _lib.check(lib.cave_plan_offset(B, m, d, ctypes.byref(off)))
+        words = self.buf[off.value:off.value + 64].cpu().view(torch.int64).tolist()
+        arr = (ctypes.c_uint64 * 8)(*[w & 0xFFFFFFFFFFFFFFFF for w in words])
+        t, c, sm = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        idx = lib.cave_plan_choice(arr, d, _lib.F64 if io_dtype == torch.float64 else _lib.F32,
+                                   _lib.F32 if precision == "fp32" else _lib.F64, ctypes.byref(t), ctypes.byref(c), ctypes.byref(sm))
+        n = max(words[0], 1)
+        return {"config": idx, "threads": t.value, "ctas_per_sm": c.value, "smem_bytes": sm.value,
+                "avg_work_bytes_f64": words[1] / n, "avg_work_bytes_f32": words[2] / n,
+                "max_hot_bytes_f64": words[3], "max_hot_bytes_f32": words[4]}
+
 
 def pack_constraints(tight_ctrs: torch.Tensor, m_rows: torch.Tensor | None = None, keep_dense: bool = True) -> CavePack:
     lib = _lib.load()

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CAVE_B200_ABI_VERSION 2
+#define CAVE_B200_ABI_VERSION 3
 
 /* error codes */
 #define CAVE_OK 0
@@ -98,6 +98,15 @@ int cave_get_limits(cave_limits* out);
  * singleton cone types, average normal).  Replaces what `_average_ctrs` (src/cave.py:222-228)
  * and the row mask of `_project_nnls` (src/cave.py:303) recompute on every call. */
 int cave_pack_bytes(int64_t B, int64_t m_max, int64_t d, size_t* out);
+
+/* Diagnostics for the solve kernel's launch plan.  cave_pack() ends with a small kernel that reduces the
+ * instances' shared-memory footprints into 8 uint64 statistics stored in the pack at cave_plan_offset(); the solve
+ * kernel is enqueued in every candidate configuration and the statistics select one ON THE DEVICE (no host
+ * round trip).  cave_plan_choice() applies the same rule to a host copy of those 8 words and returns the index
+ * of the configuration that runs (threads per CTA, CTAs per SM, dynamic shared memory per CTA). */
+int cave_plan_offset(int64_t B, int64_t m_max, int64_t d, size_t* out);
+int cave_plan_choice(const uint64_t* plan_host, int64_t d, int io_dtype, int compute_dtype,
+                     int* threads, int* ctas_per_sm, int* smem_bytes);
 
 /* Bytes of solver scratch (per-CTA sparse rows, Hessian, vectors, work counter). */
 int cave_scratch_bytes(int64_t B, int64_t m_max, int64_t d, int compute_dtype,

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_version_limits_and_sizes(lib):
     from cave_b200 import _lib
-    assert lib.cave_abi_version() == 2
+    assert lib.cave_abi_version() == 3
     lim = _lib.Limits()
     assert lib.cave_get_limits(ctypes.byref(lim)) == 0
     assert lim.max_d >= 4950 and lim.max_m >= 5200

@@ -186,6 +186,52 @@ CAVE_DEV void chol_solve(Ctx& cx, const T* L, int n, int ld, const T* diagL, T* 
 // invd[j] receives 1/d_j.  Panels of 8 columns: warp 0 factors a panel entirely in registers
 // (rows on lanes, shuffles for the pivot column), then all warps apply the rank-8 update to the
 // trailing block — two CTA barriers per panel instead of one or two per column.
+#ifndef CAVE_HOST_SIM
+// One panel of ldlt_blocked, by one warp: rows j0 + lane (+ 32) in registers, NS = 1 when no row lies beyond j0 + 31.
+// Entries above the diagonal (and columns >= pw) are loaded as zero and then left to collect garbage: nothing valid
+// ever reads them and they are not stored, which keeps the elimination free of per-element predicates.
+template <class TH, class PL, int NS>
+CAVE_DEV void ldlt_panel(Ctx& cx, PL L, int nf, PL invd, TH piv_floor, int j0, int pw) {
+    constexpr int PB = 8;
+    TH a[NS][PB];
+    int cmax[NS];                 // row i holds the valid columns c < cmax (its part of the lower triangle / the rhs row)
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const int i = j0 + cx.lane + 32 * s;
+        const int w = i == nf ? pw : (i - j0 + 1 < pw ? i - j0 + 1 : pw);
+        cmax[s] = i <= nf ? w : 0;
+        const PL li = L + (tri(i <= nf ? i : nf) + j0);
+#pragma unroll
+        for (int c = 0; c < PB; ++c) a[s][c] = c < cmax[s] ? (TH)li[c] : (TH)0;
+    }
+#pragma unroll
+    for (int jj = 0; jj < PB; ++jj) {
+        if (jj < pw) {
+            const TH dj = __shfl_sync(0xffffffffu, a[0][jj], jj);
+            const TH inv = fast_rcp(dj > piv_floor ? dj : piv_floor);
+            if (cx.lane == 0) invd[j0 + jj] = inv;
+            TH pc[PB];
+#pragma unroll
+            for (int c = jj + 1; c < PB; ++c) pc[c] = __shfl_sync(0xffffffffu, a[0][jj], c);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const TH f = a[s][jj] * inv;
+#pragma unroll
+                for (int c = jj + 1; c < PB; ++c) a[s][c] -= f * pc[c];
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const int i = j0 + cx.lane + 32 * s;
+        const PL li = L + (tri(i <= nf ? i : nf) + j0);
+#pragma unroll
+        for (int c = 0; c < PB; ++c)
+            if (c < cmax[s]) li[c] = a[s][c];
+    }
+}
+#endif
+
 template <class TH, class PL>
 CAVE_DEV void ldlt_blocked(Ctx& cx, PL L, int nf, PL invd, TH piv_floor) {
     constexpr int PB = 8;
@@ -207,42 +253,8 @@ CAVE_DEV void ldlt_blocked(Ctx& cx, PL L, int nf, PL invd, TH piv_floor) {
                     }
                 }
 #else
-                TH a[2][PB];
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const int i = j0 + cx.lane + 32 * s;
-#pragma unroll
-                    for (int c = 0; c < PB; ++c)
-                        a[s][c] = (i <= nf && c < pw && (j0 + c <= i || i == nf)) ? (TH)L[tri(i) + j0 + c] : (TH)0;
-                }
-#pragma unroll
-                for (int jj = 0; jj < PB; ++jj) {
-                    if (jj < pw) {
-                        TH dj = __shfl_sync(0xffffffffu, a[0][jj], jj);
-                        const TH inv = fast_rcp(dj > piv_floor ? dj : piv_floor);
-                        if (cx.lane == 0) invd[j0 + jj] = inv;
-                        TH pc[PB];
-#pragma unroll
-                        for (int c = jj + 1; c < PB; ++c) pc[c] = __shfl_sync(0xffffffffu, a[0][jj], c);
-#pragma unroll
-                        for (int s = 0; s < 2; ++s) {
-                            const int i = j0 + cx.lane + 32 * s;
-                            if (i > j0 + jj && i <= nf) {
-                                const TH f = a[s][jj] * inv;
-#pragma unroll
-                                for (int c = jj + 1; c < PB; ++c)
-                                    if (c < pw && (j0 + c <= i || i == nf)) a[s][c] -= f * pc[c];
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const int i = j0 + cx.lane + 32 * s;
-#pragma unroll
-                    for (int c = 0; c < PB; ++c)
-                        if (i <= nf && c < pw && (j0 + c <= i || i == nf)) L[tri(i) + j0 + c] = a[s][c];
-                }
+                if (j0 + Ctx::WS <= nf) ldlt_panel<TH, PL, 2>(cx, L, nf, invd, piv_floor, j0, pw);
+                else ldlt_panel<TH, PL, 1>(cx, L, nf, invd, piv_floor, j0, pw);
 #endif
             }
             cx.sync();
@@ -814,6 +826,36 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<TC, HOT>
         // back substitution D L^T x = z by warp 0 (column oriented, no reductions, no divisions)
         if (cx.warp == 0) {
             const HPtr<TH, HOT> z = W.L + tri(nf);
+#ifndef CAVE_HOST_SIM
+            if (nf <= 2 * Ctx::WS) {
+                // z, 1/d and the solution stay in registers (two per lane); one shuffle per step broadcasts x_j and the
+                // next row of L is fetched while the current one is applied
+                const int l = cx.lane;
+                TH z0 = l < nf ? (TH)z[l] : (TH)0, z1 = l + 32 < nf ? (TH)z[l + 32] : (TH)0;
+                const TH d0 = l < nf ? (TH)invd[l] : (TH)0, d1 = l + 32 < nf ? (TH)invd[l + 32] : (TH)0;
+                TH x0 = (TH)0, x1 = (TH)0;
+                int j = nf - 1;
+                HPtr<TH, HOT> row = W.L + tri(j);
+                TH l0 = l < j ? (TH)row[l] : (TH)0, l1 = l + 32 < j ? (TH)row[l + 32] : (TH)0;
+                for (; j >= 0; --j) {
+                    const int jn = j - 1;
+                    TH n0 = (TH)0, n1 = (TH)0;
+                    if (jn > 0) {
+                        const HPtr<TH, HOT> rn = W.L + tri(jn);
+                        n0 = l < jn ? (TH)rn[l] : (TH)0;
+                        if (jn > 32) n1 = l + 32 < jn ? (TH)rn[l + 32] : (TH)0;
+                    }
+                    const TH t = (j & 32) ? z1 * d1 : z0 * d0;
+                    const TH xj = __shfl_sync(0xffffffffu, t, j & 31);
+                    if (l == (j & 31)) { if (j & 32) x1 = xj; else x0 = xj; }
+                    z0 -= l0 * xj;
+                    if (j > 32) z1 -= l1 * xj;
+                    l0 = n0; l1 = n1;
+                }
+                if (l < nf) W.dir[(int)W.flist[l]] = (T)x0;
+                if (l + 32 < nf) W.dir[(int)W.flist[l + 32]] = (T)x1;
+            } else
+#endif
             for (int j = nf - 1; j >= 0; --j) {
                 const TH xj = (TH)z[j] * (TH)invd[j];
                 cx.syncwarp();

@@ -342,6 +342,7 @@ struct NewtonWork {
     HPtr<int, HOT> fpos;                          // variable -> position in flist or -1
     int* cur;                                     // [d] CSC fill cursors (setup only)
     HPtr<uint8_t, HOT> wflag;                     // [d] psi'(r_k) currently folded into H
+    HPtr<uint8_t, HOT> act;                       // [d] psi'(r_k) of the last evaluated point
     HPtr<TH, HOT> H;                              // [nv, nv] lower triangle of B W B^T, kept up to date
     HPtr<int, HOT> Hi;                            // ... as exact 32-bit integers when the rows are int8 (i8)
     HPtr<TH, HOT> L;                              // [(nf+1), ldl] LDL^T work array with the rhs as last row
@@ -354,19 +355,24 @@ CAVE_DEV void nw_eval2_t(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, H
     T acc = (T)0;
     for (int k = cx.tid; k < W.d; k += cx.nthr) {
         T rk = (T)(TC)W.c[k];
-        int e = W.cptr[k];
         const int e1 = W.cptr[k + 1];
-        // four gathers in flight per thread (the shared-memory accessors are ordered, so the compiler will
-        // not overlap them by itself); the subtraction order is unchanged
-        for (; e + 4 <= e1; e += 4) {
-            const int i0 = W.crow[e], i1 = W.crow[e + 1], i2 = W.crow[e + 2], i3 = W.crow[e + 3];
-            const T v0 = (T)cval[e], v1 = (T)cval[e + 1], v2 = (T)cval[e + 2], v3 = (T)cval[e + 3];
+        // four gathers in flight per thread (the shared-memory accessors are ordered, so the compiler will not
+        // overlap them by itself); entries past the column end are read as 0 * nu[0]: the subtraction order and
+        // the result are those of the plain loop
+        for (int e = W.cptr[k]; e < e1; e += 4) {
+            const bool p1 = e + 1 < e1, p2 = e + 2 < e1, p3 = e + 3 < e1;
+            const int i0 = W.crow[e], i1 = p1 ? W.crow[e + 1] : 0, i2 = p2 ? W.crow[e + 2] : 0, i3 = p3 ? W.crow[e + 3] : 0;
+            const T v0 = (T)cval[e], v1 = p1 ? (T)cval[e + 1] : (T)0, v2 = p2 ? (T)cval[e + 2] : (T)0, v3 = p3 ? (T)cval[e + 3] : (T)0;
             const T n0 = nu[i0], n1 = nu[i1], n2 = nu[i2], n3 = nu[i3];
             rk -= v0 * n0; rk -= v1 * n1; rk -= v2 * n2; rk -= v3 * n3;
         }
-        for (; e < e1; ++e) rk -= (T)cval[e] * (T)nu[W.crow[e]];
-        rout[k] = rk;
-        T q = psi(rk, (int)(uint8_t)W.ctype[k]);
+        // the array holds q = psi(r) (all that the gradient and the epilogue need; psi is idempotent) and the
+        // activity flag psi'(r) goes to its own byte array for the Hessian update
+        const int t = (int)(uint8_t)W.ctype[k];
+        const bool on = psi_active(rk, t);
+        const T q = on ? rk : (T)0;
+        rout[k] = q;
+        W.act[k] = (uint8_t)(on ? 1 : 0);
         acc += q * q;
     }
     cx.block_sum2(acc, extra);
@@ -391,13 +397,12 @@ CAVE_DEV T nw_grad_t(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HOT> 
         for (; e + 3 * Ctx::WS < e1; e += 4 * Ctx::WS) {       // four gathers in flight per lane, same order
             const int k0 = W.rcol[e], k1 = W.rcol[e + Ctx::WS], k2 = W.rcol[e + 2 * Ctx::WS], k3 = W.rcol[e + 3 * Ctx::WS];
             const T v0 = (T)rval[e], v1 = (T)rval[e + Ctx::WS], v2 = (T)rval[e + 2 * Ctx::WS], v3 = (T)rval[e + 3 * Ctx::WS];
-            const T r0 = r[k0], r1 = r[k1], r2 = r[k2], r3 = r[k3];
-            const int t0 = (int)(uint8_t)W.ctype[k0], t1 = (int)(uint8_t)W.ctype[k1], t2 = (int)(uint8_t)W.ctype[k2], t3 = (int)(uint8_t)W.ctype[k3];
-            acc += v0 * psi(r0, t0); acc += v1 * psi(r1, t1); acc += v2 * psi(r2, t2); acc += v3 * psi(r3, t3);
+            const T r0 = r[k0], r1 = r[k1], r2 = r[k2], r3 = r[k3];          // r holds psi(r) already (nw_eval2)
+            acc += v0 * r0; acc += v1 * r1; acc += v2 * r2; acc += v3 * r3;
         }
         for (; e < e1; e += Ctx::WS) {
             int k = W.rcol[e];
-            acc += (T)rval[e] * psi((T)r[k], (int)(uint8_t)W.ctype[k]);
+            acc += (T)rval[e] * (T)r[k];
         }
         acc = cx.warp_sum(acc);
         const T gv = -acc, nv_ = nu[v];
@@ -426,7 +431,7 @@ CAVE_DEV void nw_hessian_update_t(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, 
     const VT* cval = (const VT*)W.cval;
     const int nv = W.nv;
     for (int k = cx.tid; k < W.d; k += cx.nthr) {
-        const uint8_t now = psi_active((T)r[k], (int)(uint8_t)W.ctype[k]) ? 1 : 0;
+        const uint8_t now = (uint8_t)W.act[k];
         if (now == (uint8_t)W.wflag[k]) continue;
         W.wflag[k] = now;
         const int s = W.cptr[k], e = W.cptr[k + 1];
@@ -494,6 +499,7 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     W.fpos = ar.geth<HOT, int>(mB + 2);
     W.vfree = ar.geth<HOT, uint8_t>(mB + 1);
     W.wflag = ar.geth<HOT, uint8_t>(d + 1);
+    W.act = ar.geth<HOT, uint8_t>(d + 1);
     HPtr<uint8_t, HOT> ctype_s = ar.geth<HOT, uint8_t>(d + 1);
     W.rptr = ar.get<int>(mB + 2);
     W.vrow = ar.get<int>(mB + 1);

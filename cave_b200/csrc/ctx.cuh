@@ -51,6 +51,7 @@ struct HPtr {
     HPtr operator+(size_t o) const { return HPtr(p + o); }
     U* raw() const { return p; }
     void atomic_add(size_t i, U v) const { p[i] += v; }
+    U fetch_add(size_t i, U v) const { U o = p[i]; p[i] += v; return o; }
 };
 }  // namespace cave
 #else
@@ -179,6 +180,13 @@ template <> struct SmemOps<int> {
     static __device__ __forceinline__ int ld(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
     static __device__ __forceinline__ void st(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
     static __device__ __forceinline__ void add(uint32_t a, int v) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+    static __device__ __forceinline__ int fetch_add(uint32_t a, int v) { int o; asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
+};
+template <> struct SmemOps<uint16_t> {
+    static __device__ __forceinline__ uint16_t ld(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return (uint16_t)v; }
+    static __device__ __forceinline__ void st(uint32_t a, uint16_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"((uint32_t)v) : "memory"); }
+    static __device__ __forceinline__ void add(uint32_t, uint16_t) {}
+    static __device__ __forceinline__ uint16_t fetch_add(uint32_t, uint16_t) { return 0; }
 };
 template <> struct SmemOps<uint8_t> {
     static __device__ __forceinline__ uint8_t ld(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return (uint8_t)v; }
@@ -203,6 +211,7 @@ template <class U> struct HPtr<U, true> {
     __device__ __forceinline__ HPtr operator+(uint32_t o) const { HPtr h; h.a = a + o * (uint32_t)sizeof(U); return h; }
     __device__ __forceinline__ U* raw() const { return (U*)__cvta_shared_to_generic((size_t)a); }
     __device__ __forceinline__ void atomic_add(uint32_t i, U v) const { SmemOps<U>::add(a + i * (uint32_t)sizeof(U), v); }
+    __device__ __forceinline__ U fetch_add(uint32_t i, U v) const { return SmemOps<U>::fetch_add(a + i * (uint32_t)sizeof(U), v); }
 };
 template <class U> struct HPtr<U, false> {
     U* p;
@@ -212,6 +221,7 @@ template <class U> struct HPtr<U, false> {
     __device__ __forceinline__ HPtr operator+(size_t o) const { return HPtr(p + o); }
     __device__ __forceinline__ U* raw() const { return p; }
     __device__ __forceinline__ void atomic_add(size_t i, U v) const { atomicAdd(p + i, v); }
+    __device__ __forceinline__ U fetch_add(size_t i, U v) const { return atomicAdd(p + i, v); }
 };
 
 // streaming global load that does not pollute L1 (rows of A are touched once per phase)

@@ -91,7 +91,7 @@ CAVE_HD void instance_footprint(int64_t d, int64_t ngen, int64_t nv, int64_t nnz
         size_t w = h + 2 * a16(D * 8) + 2 * a16(k * k * 8) + 8 * a16(k * 8) + a16(M * 5);
         *hot = h; *work = w; return;
     }
-    h += 4 * a16((M + 1) * 8) + a16((2 * M + 6) * th) + 256 + 2 * a16((M + 2) * 4) + a16(M + 1) + 3 * a16(D + 1);
+    h += 4 * a16((M + 1) * 8) + a16((2 * M + 6) * th) + 256 + 2 * a16((M + 2) * 4) + a16(M + 1) + 3 * a16(D + 1) + a16((D + 1) * 2) + 16;
     h += a16((V * (V + 1) / 2 + 1) * (i8 ? 4 : th)) + a16(((V + 2) * (V + 3) / 2 + 1) * th);
     size_t w = h + a16((M + 2) * 4) + a16((M + 1) * 4) + a16((D + 2) * 4) + a16((Z + 1) * 2) + a16((Z + 1) * (i8 ? 1 : 4));
     w += (a16((Z + 8) * 2) + a16((Z + 4) * (i8 ? 1 : 4))) / 2;        // half of the CSR: spilling it costs little, not nothing
@@ -120,7 +120,7 @@ struct ScratchLayout {
 CAVE_HD size_t solver_slot_bytes(int64_t d, int64_t cap_rows, int64_t cap_nnz, size_t T) {
     const size_t r = (size_t)cap_rows + 2, dd = (size_t)d + 2;
     // Newton path (upper bound over every Arena::get in nw_setup / newton_solve)
-    size_t nw = 3 * dd * T + 4 * dd + 4 * dd + 2 * dd + r * (6 * T + 4 + 4 + 1 + 4 + 1 + 4 + 4 + 8 + 4)
+    size_t nw = 3 * dd * T + 4 * dd + 4 * dd + 4 * dd + 64 + r * (6 * T + 4 + 4 + 1 + 4 + 1 + 4 + 4 + 8 + 4)
               + (size_t)(cap_nnz + 2) * 12 + (r * (r + 1) / 2 + (r + 2) * (r + 3) / 2 + 8) * T;
     // Lawson-Hanson path
     const size_t k = (cap_rows < d ? (size_t)cap_rows : (size_t)d) + 2;

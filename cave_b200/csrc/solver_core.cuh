@@ -343,6 +343,8 @@ struct NewtonWork {
     int* cur;                                     // [d] CSC fill cursors (setup only)
     HPtr<uint8_t, HOT> wflag;                     // [d] psi'(r_k) currently folded into H
     HPtr<uint8_t, HOT> act;                       // [d] psi'(r_k) of the last evaluated point
+    HPtr<uint16_t, HOT> flipk;                    // [d] coordinates whose activity changed (bit 15: now active)
+    HPtr<int, HOT> fcnt;                          // [1] length of flipk, zero between Hessian updates
     HPtr<TH, HOT> H;                              // [nv, nv] lower triangle of B W B^T, kept up to date
     HPtr<int, HOT> Hi;                            // ... as exact 32-bit integers when the rows are int8 (i8)
     HPtr<TH, HOT> L;                              // [(nf+1), ldl] LDL^T work array with the rhs as last row
@@ -429,37 +431,52 @@ CAVE_DEV T nw_grad(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HOT> r,
 template <class VT, class T, class TH, class TC, bool HOT>
 CAVE_DEV void nw_hessian_update_t(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HOT> r) {
     const VT* cval = (const VT*)W.cval;
-    const int nv = W.nv;
-    for (int k = cx.tid; k < W.d; k += cx.nthr) {
-        const uint8_t now = (uint8_t)W.act[k];
-        if (now == (uint8_t)W.wflag[k]) continue;
-        W.wflag[k] = now;
-        const int s = W.cptr[k], e = W.cptr[k + 1];
-        if (sizeof(VT) == 1) {       // int8 rows: H is an exact integer matrix (|H_ij| <= 127^2 d < 2^31)
-            const int sg = now ? 1 : -1;
-            for (int e1 = s; e1 < e; ++e1) {
-                const int a = W.crow[e1];
-                const int va = sg * (int)cval[e1];
-                for (int e2 = s; e2 <= e1; ++e2) {
-                    const int b = W.crow[e2];
-                    const int hi = a > b ? a : b, lo = a > b ? b : a;
-                    W.Hi.atomic_add(tri(hi) + lo, va * (int)cval[e2]);
-                }
-            }
-        } else {
-            const TH sg = now ? (TH)1 : (TH)-1;
-            for (int e1 = s; e1 < e; ++e1) {
-                const int a = W.crow[e1];
-                const TH va = sg * (TH)cval[e1];
-                for (int e2 = s; e2 <= e1; ++e2) {
-                    const int b = W.crow[e2];
-                    const int hi = a > b ? a : b, lo = a > b ? b : a;
-                    W.H.atomic_add(tri(hi) + lo, va * (TH)cval[e2]);
-                }
-            }
+    // phase 1: the coordinates whose activity changed, compacted into a list (order irrelevant: the integer
+    // Hessian is exact, and a float Hessian was order dependent before as well)
+    for (int k0 = 0; k0 < W.d; k0 += cx.nthr) {
+        const int k = k0 + cx.tid;
+        bool flip = false;
+        uint8_t now = 0;
+        if (k < W.d) {
+            now = (uint8_t)W.act[k];
+            flip = now != (uint8_t)W.wflag[k];
+            if (flip) W.wflag[k] = now;
+        }
+        const unsigned m = cx.ballot(flip);
+        if (m) {
+            int base = 0;
+            if (cx.lane == 0) base = W.fcnt.fetch_add(0, cx.popc(m));
+            base = cx.shfl(base, 0);
+            if (flip) W.flipk[base + cx.lanes_below(m)] = (uint16_t)(k | (now ? 0x8000 : 0));
         }
     }
     cx.sync();
+    const int n = W.fcnt[0];
+    // phase 2: G threads per flipped column (G a power of two, about nthr / n) share its pairs, so a handful
+    // of flips late in the solve still occupies whole warps and thousands of them in the first iterations
+    // are spread one per thread
+    int G = 1;
+    while (G < Ctx::WS && n * (G * 2) <= cx.nthr) G *= 2;
+    const int sub = cx.tid & (G - 1);
+    for (int fi = cx.tid / G; fi < n; fi += cx.nthr / G) {
+        const int kk = (int)(uint16_t)W.flipk[fi];
+        const int k = kk & 0x3fff;
+        const int s = W.cptr[k], cnt = W.cptr[k + 1] - s;
+        const int sgi = (kk & 0x8000) ? 1 : -1;
+        // pair p <-> (e1 >= e2): walk the rows of the triangle, starting where this thread's first pair lies
+        int e1 = 0, rowstart = 0;
+        const int npairs = (cnt * (cnt + 1)) >> 1;
+        for (int p = sub; p < npairs; p += G) {
+            while (rowstart + e1 + 1 <= p) { rowstart += e1 + 1; ++e1; }
+            const int e2 = p - rowstart;
+            const int a = W.crow[s + e1], b = W.crow[s + e2];
+            const int hi = a > b ? a : b, lo = a > b ? b : a;
+            if (sizeof(VT) == 1) W.Hi.atomic_add(tri(hi) + lo, sgi * (int)cval[s + e1] * (int)cval[s + e2]);
+            else W.H.atomic_add(tri(hi) + lo, ((TH)sgi * (TH)cval[s + e1]) * (TH)cval[s + e2]);
+        }
+    }
+    cx.sync();
+    if (cx.tid == 0) W.fcnt[0] = 0;       // invariant: zero between calls (the next use is several barriers away)
 }
 template <class T, class TH, class TC, bool HOT>
 CAVE_DEV void nw_hessian_update(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HOT> r) {
@@ -500,6 +517,8 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
     W.vfree = ar.geth<HOT, uint8_t>(mB + 1);
     W.wflag = ar.geth<HOT, uint8_t>(d + 1);
     W.act = ar.geth<HOT, uint8_t>(d + 1);
+    W.flipk = ar.geth<HOT, uint16_t>(d + 1);
+    W.fcnt = ar.geth<HOT, int>(4);
     HPtr<uint8_t, HOT> ctype_s = ar.geth<HOT, uint8_t>(d + 1);
     W.rptr = ar.get<int>(mB + 2);
     W.vrow = ar.get<int>(mB + 1);
@@ -525,6 +544,7 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
         for (int u = 0; u < 8; ++u) { const int k = k0 + u * cx.nthr + cx.tid; if (k < d) { ctype_s[k] = t[u]; W.wflag[k] = 0; } }
     }
     W.ctype = ctype_s;
+    if (cx.tid == 0) W.fcnt[0] = 0;
     for (int i = cx.tid; i < mB; i += cx.nthr) {
         gen_t g = in.gen[i]; W.grow[i] = g.x; gcnt[i] = g.y; goff[i] = g.z;
         if (in.csr_ok) { hash_t h = in.ghash[g.x]; hpos[i] = h.x; hneg[i] = h.y; }

@@ -105,15 +105,27 @@ template <class T> CAVE_DEV T psi(T r, int t) { return psi_active(r, t) ? r : (T
 template <class T> CAVE_DEV T cabs(T v) { return v < (T)0 ? -v : v; }
 // start of row i in a row-packed lower triangle (row i holds columns 0..i)
 CAVE_DEV uint32_t tri(int i) { return ((uint32_t)i * (uint32_t)(i + 1)) >> 1; }
-// reciprocal of a positive pivot without a full-precision division on the critical path
-CAVE_DEV float fast_rcp(float x) { return 1.0f / x; }
+// Reciprocal of a positive pivot: it sits on the critical path of every LDL^T column.  Measured dependent latency
+// on B200 (tools/ubench/rcp.cu): 1.0/x 80 cycles, MUFU seed + Newton steps 47 (f64, full precision) / 22 (f32).
+CAVE_DEV float fast_rcp(float x) {
+#ifdef CAVE_HOST_SIM
+    return 1.0f / x;
+#else
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    const float e = fmaf(-x, y, 1.0f);
+    return fmaf(y, e, y);
+#endif
+}
 CAVE_DEV double fast_rcp(double x) {
 #ifdef CAVE_HOST_SIM
     return 1.0 / x;
 #else
-    double y = (double)__frcp_rn((float)x);      // 24 bits
-    y = y * (2.0 - x * y);                        // 48 bits
-    return y * (2.0 - x * y);                     // full
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));     // >= 20 bits
+    double e = fma(-x, y, 1.0); y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
 #endif
 }
 template <class T> CAVE_DEV T eps_mach();
@@ -859,27 +871,30 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<TC, HOT>
                 const int l = cx.lane;
                 TH z0 = l < nf ? (TH)z[l] : (TH)0, z1 = l + 32 < nf ? (TH)z[l + 32] : (TH)0;
                 const TH d0 = l < nf ? (TH)invd[l] : (TH)0, d1 = l + 32 < nf ? (TH)invd[l + 32] : (TH)0;
-                TH x0 = (TH)0, x1 = (TH)0;
                 int j = nf - 1;
-                HPtr<TH, HOT> row = W.L + tri(j);
-                TH l0 = l < j ? (TH)row[l] : (TH)0, l1 = l + 32 < j ? (TH)row[l + 32] : (TH)0;
-                for (; j >= 0; --j) {
-                    const int jn = j - 1;
-                    TH n0 = (TH)0, n1 = (TH)0;
-                    if (jn > 0) {
-                        const HPtr<TH, HOT> rn = W.L + tri(jn);
-                        n0 = l < jn ? (TH)rn[l] : (TH)0;
-                        if (jn > 32) n1 = l + 32 < jn ? (TH)rn[l + 32] : (TH)0;
-                    }
-                    const TH t = (j & 32) ? z1 * d1 : z0 * d0;
-                    const TH xj = __shfl_sync(0xffffffffu, t, j & 31);
-                    if (l == (j & 31)) { if (j & 32) x1 = xj; else x0 = xj; }
-                    z0 -= l0 * xj;
-                    if (j > 32) z1 -= l1 * xj;
-                    l0 = n0; l1 = n1;
+                uint32_t tj = tri(j);                       // start of row j; row j - 1 starts j entries earlier
+                TH l0 = l < j ? (TH)W.L[tj + l] : (TH)0, l1 = l + 32 < j ? (TH)W.L[tj + l + 32] : (TH)0;
+                // rows 32 .. nf-1: x_j comes from the upper register, both halves of z are updated
+                for (; j >= 32; --j) {
+                    const uint32_t tn = tj - (uint32_t)j;
+                    const TH n0 = l < j - 1 ? (TH)W.L[tn + l] : (TH)0;
+                    const TH n1 = l + 32 < j - 1 ? (TH)W.L[tn + l + 32] : (TH)0;
+                    const TH xj = __shfl_sync(0xffffffffu, z1 * d1, j & 31);
+                    if (l == 0) z[j] = xj;                  // the solution overwrites z in place
+                    z0 -= l0 * xj; z1 -= l1 * xj;
+                    l0 = n0; l1 = n1; tj = tn;
                 }
-                if (l < nf) W.dir[(int)W.flist[l]] = (T)x0;
-                if (l + 32 < nf) W.dir[(int)W.flist[l + 32]] = (T)x1;
+                for (; j >= 0; --j) {
+                    const uint32_t tn = tj - (uint32_t)j;
+                    const TH n0 = l < j - 1 ? (TH)W.L[tn + l] : (TH)0;
+                    const TH xj = __shfl_sync(0xffffffffu, z0 * d0, j);
+                    if (l == 0) z[j] = xj;
+                    z0 -= l0 * xj;
+                    l0 = n0; tj = tn;
+                }
+                cx.syncwarp();
+                if (l < nf) W.dir[(int)W.flist[l]] = (T)(TH)z[l];
+                if (l + 32 < nf) W.dir[(int)W.flist[l + 32]] = (T)(TH)z[l + 32];
             } else
 #endif
             for (int j = nf - 1; j >= 0; --j) {

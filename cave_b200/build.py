@@ -10,8 +10,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libcave_b200.so")
-SOURCES = ["scan_kernel.cu", "solve_kernel.cu", "abi.cu"]
-HEADERS = ["ctx.cuh", "layout.cuh", "scan_kernel.cuh", "solve_kernel.cuh", "solver_core.cuh",
+SOURCES = ["scan_kernel.cu", "solve_kernel.cu", "solve_inst_f32_f32.cu", "solve_inst_f32_f64.cu",
+           "solve_inst_f64_f32.cu", "solve_inst_f64_f64.cu", "abi.cu"]
+HEADERS = ["ctx.cuh", "layout.cuh", "scan_kernel.cuh", "solve_kernel.cuh", "solve_kernel_impl.cuh", "solver_core.cuh",
            os.path.join("..", "..", "include", "cave_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -40,7 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for s in SOURCES:
         obj = os.path.join(OUT_DIR, s.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", obj]
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("CAVE_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, s), "-o", obj]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for s, pr in procs:

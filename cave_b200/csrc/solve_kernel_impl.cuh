@@ -1,0 +1,61 @@
+// Solve kernel template and its launcher; instantiated once per (factor dtype, I/O dtype) in solve_inst_*.cu so
+// that the four variants compile in parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "layout.cuh"
+#include "solve_kernel.cuh"
+#include "solver_core.cuh"
+
+namespace cave {
+
+template <class T, class TIO>
+__global__ void __launch_bounds__(256, 2) solve_kernel(SolveParams p) {
+    extern __shared__ __align__(16) char smem[];
+    __shared__ double red[64];
+    __shared__ int s_b;
+    if (p.cfg_id >= 0 && choose_solve_config(p.plan, sizeof(T), sizeof(TIO) == 8 ? (size_t)p.d * 4 : 0) != p.cfg_id) return;
+    Ctx cx(red);
+    char* slot = p.slots + (size_t)blockIdx.x * p.slot_bytes;
+    EpiParams ep; ep.mode = p.mode; ep.inner_ratio = p.inner_ratio; ep.sign = p.sign; ep.gscale = p.gscale;
+    SolveOpts opt; opt.max_iter = p.max_iter; opt.max_ls = p.max_ls; opt.tol = p.tol;
+    const TIO* pred = (const TIO*)p.pred;
+    TIO* grad = (TIO*)p.grad;
+    TIO* proj = (TIO*)p.proj;
+    for (;;) {
+        if (cx.tid == 0) s_b = atomicAdd(p.counter, 1);
+        __syncthreads();
+        const int b = s_b;
+        __syncthreads();
+        if (b >= p.B) break;
+        const size_t q = p.inst_index ? (size_t)p.inst_index[b] : (size_t)b;     // instance of the pack / of A
+        Instance in;
+        in.A = p.A ? p.A + q * p.m_max * p.d : nullptr;
+        in.gen = p.gen + q * p.m_max;
+        in.ctype = p.ctype + q * p.dpad;
+        in.avg = p.avg + q * p.dpad;
+        in.d = p.d; in.ngen = p.ngen[q]; in.gen_nnz = p.gennnz[q]; in.nvalid = p.nvalid[q]; in.nsingc = p.nsingc[q];
+        in.csr_ok = p.csr_ok[q]; in.maxl1 = p.maxl1[q]; in.maxl2 = p.maxl2[q];
+        in.ghash = p.ghash + q * p.m_max;
+        in.pcol = p.csr_col + q * p.cap_nnz;
+        in.pval = p.csr_val + q * p.cap_nnz;
+        solve_instance<T, TIO>(cx, in, smem, (size_t)p.smem_bytes, slot, p.slot_bytes, pred + (size_t)b * p.d, ep, opt, grad + (size_t)b * p.d,
+                               proj ? proj + (size_t)b * p.d : nullptr, p.loss64 + b, p.rnorm64 + b,
+                               p.status + b, p.iters + b);
+        __syncthreads();
+    }
+}
+
+template <class T, class TIO>
+cudaError_t launch_solve_t(const SolveParams& p, int grid, int threads, cudaStream_t stream) {
+    static int configured = 0;
+    if (configured < p.smem_bytes) {
+        cudaError_t e = cudaFuncSetAttribute(solve_kernel<T, TIO>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes);
+        if (e != cudaSuccess) return e;
+        configured = p.smem_bytes;
+    }
+    solve_kernel<T, TIO><<<grid, threads, p.smem_bytes, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace cave

@@ -247,8 +247,8 @@ def run_ours(args):
     # step-level roofline: algorithmic bytes of the whole path over the whole step, against HBM
     achieved = alg_bytes / ms_step / 1e6
     # DRAM bytes per step from the ncu --set full capture of this command (profiles/r1_ncu_summary.txt):
-    # scan 26.883 + 0.223 GB, solve 0.241 + 0.017 GB; only valid for the default workload
-    traffic = 27.364e9 if (args.workload == "tsp50" and B == 4096) else None
+    # scan 26.884 + 0.223 GB, plan 0.015 GB, solve 0.240 + 0.027 GB; only valid for the default workload
+    traffic = 27.39e9 if (args.workload == "tsp50" and B == 4096) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": peak_src, "dominant_kernel": dom["name"],
                 "algorithmic_bytes_per_step": alg_bytes,

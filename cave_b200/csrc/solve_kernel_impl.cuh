@@ -1,6 +1,10 @@
 // Solve kernel template and its launcher; instantiated once per (factor dtype, I/O dtype) in solve_inst_*.cu so
 // that the four variants compile in parallel.
 #pragma once
+#ifndef CAVE_LB_T
+#define CAVE_LB_T 256      // launch bounds of the solve kernel: 256 x 2 = 128 registers per thread
+#define CAVE_LB_C 2
+#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "layout.cuh"
@@ -10,7 +14,7 @@
 namespace cave {
 
 template <class T, class TIO>
-__global__ void __launch_bounds__(256, 2) solve_kernel(SolveParams p) {
+__global__ void __launch_bounds__(CAVE_LB_T, CAVE_LB_C) solve_kernel(SolveParams p) {
     extern __shared__ __align__(16) char smem[];
     __shared__ double red[64];
     __shared__ int s_b;

@@ -342,3 +342,33 @@ def test_sp5_end_to_end_regret_config0():
     spec.loader.exec_module(mod)
     r0, r1 = mod.run("cave-e", n_train=400, n_test=400, epochs=6, verbose=False)
     assert r1 < 0.5 * r0 and r1 < 0.25, (r0, r1)
+
+
+@pytest.mark.parametrize("kind,batch,mode", [("tsp20", 24, 1), ("sp5", 40, 0), ("tsp50", 4, 1)])
+def test_every_solve_launch_configuration_matches_the_oracle(kind, batch, mode, monkeypatch):
+    """The solve kernel is enqueued as 64x8, 128x4, 160x3 and 256x2 (threads x CTAs/SM) and the pack's plan statistics
+    pick one on the device.  Forcing each of them (CAVE_SOLVE_CFG) must give the oracle's answer — including the
+    small configurations on TSP-50, whose working set then spills to the global slot."""
+    from cave_b200 import synth
+    insts = synth.make_batch(kind, batch, seed=21)
+    ctrs, pred = synth.densify(insts).numpy(), synth.predictions(insts, 21, "near")
+    ref = O.forward_backward(pred, ctrs, mode=mode, fp64=True)
+    _check(_run(pred, ctrs, mode=mode), ref, 1e-5, mode)              # the configuration the plan selects
+    for cfg in range(4):
+        monkeypatch.setenv("CAVE_SOLVE_CFG", str(cfg))
+        _check(_run(pred, ctrs, mode=mode), ref, 1e-5, mode)
+
+
+def test_launch_plan_tracks_the_instance_size():
+    """Small instances select many small CTAs per SM, TSP-50 a wider CTA; dense (Lawson-Hanson) instances whose
+    Gram does not fit the small configurations select the widest one."""
+    from cave_b200 import pack_constraints, synth
+    dev = _cuda()
+    small = pack_constraints(synth.densify(synth.make_batch("tsp20", 16, seed=3)).to(dev)).launch_plan("fp64")
+    big = pack_constraints(synth.densify(synth.make_batch("tsp50", 4, seed=3)).to(dev)).launch_plan("fp64")
+    assert small["threads"] * small["ctas_per_sm"] >= 480 and big["threads"] * big["ctas_per_sm"] >= 480
+    assert small["smem_bytes"] < big["smem_bytes"]
+    assert small["avg_work_bytes_f64"] < big["avg_work_bytes_f64"] and small["avg_work_bytes_f32"] <= small["avg_work_bytes_f64"]
+    A, _ = synth.dense_batch(4, 256, 190, seed=5, device=dev)
+    dense = pack_constraints(A.contiguous()).launch_plan("fp64")
+    assert dense["config"] == 3

@@ -512,6 +512,36 @@ CAVE_DEV void warp0_inclusive_scan(Ctx& cx, int* x, int n) {
     }
 }
 
+// Inclusive scan of x[0..n) in place by the whole CTA: every warp scans a contiguous segment, the segment totals
+// go through scr[nwarp].  Callers synchronise before; ends with a barrier.
+CAVE_DEV void block_inclusive_scan(Ctx& cx, int* x, int n, int* scr) {
+    if (Ctx::WS == 1 || n < 8 * Ctx::WS) {
+        warp0_inclusive_scan(cx, x, n);
+        cx.sync();
+        return;
+    }
+#ifndef CAVE_HOST_SIM
+    const int seg = ((n + cx.nwarp - 1) / cx.nwarp + 31) & ~31;
+    const int s0 = cx.warp * seg, s1 = s0 + seg < n ? s0 + seg : n;
+    int carry = 0;
+    for (int i0 = s0; i0 < s1; i0 += 32) {
+        const int i = i0 + cx.lane;
+        int v = i < s1 ? x[i] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (cx.lane >= o) v += u; }
+        v += carry;
+        if (i < s1) x[i] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+    if (cx.lane == 0) scr[cx.warp] = carry;
+    cx.sync();
+    int off = 0;
+    for (int w = 0; w < cx.warp; ++w) off += scr[w];
+    if (off) for (int i = s0 + cx.lane; i < s1; i += 32) x[i] += off;
+    cx.sync();
+#endif
+}
+
 // Setup of one structured instance: merge +- rows, build the variable list, bring the CSR of the kept
 // general rows into the arena (from the scan kernel's pack, or by reading the rows of A when the pack
 // could not hold them) and build the CSC.  HOT selects shared-memory-only allocation for the arrays of
@@ -743,8 +773,7 @@ CAVE_DEV bool nw_setup(Ctx& cx, const Instance& in, Arena& ar, NewtonWork<T, TH,
         for (int e = W.rptr[row] + cx.lane; e < W.rptr[row + 1]; e += Ctx::WS) cx.atomic_add(&W.cptr[W.rcol[e] + 1], 1);
     }
     cx.sync();
-    warp0_inclusive_scan(cx, W.cptr + 1, d);
-    cx.sync();
+    block_inclusive_scan(cx, W.cptr + 1, d, (int*)W.wmax.raw());      // wmax (32 doubles) is idle during setup
     for (int k = cx.tid; k < d; k += cx.nthr) W.cur[k] = W.cptr[k];
     cx.sync();
     for (int v = cx.warp; v < nv; v += cx.nwarp) {
@@ -846,6 +875,32 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<TC, HOT>
             nf = (int)W.fpos[nv];
         }
         // L <- [H_FF + reg I ; g_F^T]
+        if (Ctx::WS == 32 && nf <= 2 * Ctx::WS) {
+            // the free list in registers (two entries per lane): one gather hop per element instead of two
+            const int l = cx.lane;
+            const int f0 = l < nf ? (int)W.flist[l] : 0, f1 = l + 32 < nf ? (int)W.flist[l + 32] : 0;
+            for (int a = cx.warp; a <= nf; a += cx.nwarp) {
+                const HPtr<TH, HOT> la = W.L + tri(a);
+                if (a == nf) {
+                    if (l < nf) la[l] = (TH)(T)W.g[f0];
+                    if (l + 32 < nf) la[l + 32] = (TH)(T)W.g[f1];
+                } else {
+                    const int fa = (int)W.flist[a];                  // flist ascending => flist[a] >= flist[b]
+                    TH h0 = (TH)0, h1 = (TH)0;
+                    if (W.i8) {
+                        const HPtr<int, HOT> ha = W.Hi + tri(fa);
+                        if (l <= a) h0 = (TH)(int)ha[f0];
+                        if (l + 32 <= a) h1 = (TH)(int)ha[f1];
+                    } else {
+                        const HPtr<TH, HOT> ha = W.H + tri(fa);
+                        if (l <= a) h0 = (TH)ha[f0];
+                        if (l + 32 <= a) h1 = (TH)ha[f1];
+                    }
+                    if (l <= a) la[l] = h0 + (a == l ? reg : (TH)0);
+                    if (l + 32 <= a) la[l + 32] = h1 + (a == l + 32 ? reg : (TH)0);
+                }
+            }
+        } else
         for (int a = cx.warp; a <= nf; a += cx.nwarp) {
             const HPtr<TH, HOT> la = W.L + tri(a);
             if (a == nf) {

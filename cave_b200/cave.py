@@ -38,7 +38,16 @@ class _CaveCudaFunction(torch.autograd.Function):
         out = cave_forward_backward(pred_cost, tight_ctrs, sign, mode, inner_ratio, reduction, **kwargs)
         grad, loss = out["grad"], out["loss"]
         if grad.device != pred_cost.device:       # host tensors in -> host tensors out
-            grad, loss = grad.to(pred_cost.device), loss.to(pred_cost.device)
+            if pred_cost.device.type == "cpu" and pred_cost.is_pinned():
+                # pinned in -> pinned out: one asynchronous copy each on the kernels' stream, one synchronisation
+                g_host = torch.empty(grad.shape, dtype=grad.dtype, pin_memory=True)
+                l_host = torch.empty(loss.shape, dtype=loss.dtype, pin_memory=True)
+                g_host.copy_(grad, non_blocking=True)
+                l_host.copy_(loss, non_blocking=True)
+                torch.cuda.current_stream(grad.device).synchronize()
+                grad, loss = g_host, l_host
+            else:
+                grad, loss = grad.to(pred_cost.device), loss.to(pred_cost.device)
         ctx.save_for_backward(grad)
         ctx.per_instance = reduction == "none"
         return loss.to(pred_cost.dtype)

@@ -340,7 +340,7 @@ def run_ours(args):
         "config": {"workload": f"{args.workload} DFJ synthetic (SURVEY App. B), CaVE+ inner_ratio {ratio}, batch {B}/GPU, "
                                f"pred regime {args.regime}, dense float32 [B,{m_max},{d}] resident in HBM, cold pack",
                    "batch_per_gpu": B, "m_max": m_max, "d": d, "l2_policy": "inputs larger than L2 (A = %.1f GB)" % (scan_bytes / 1e9)},
-        "clocks": clocks, "e2e": e2e, "e2e_resident_dataset": e2e_resident, "gpu_launches": 7 * args.steps,
+        "clocks": clocks, "e2e": e2e, "e2e_resident_dataset": e2e_resident, "gpu_launches": 8 * args.steps,
         "roofline": roofline, "kernels": kernels, "solve_launch_plan": plan_info,
         "solver": {"status_counts": {str(k): int(v) for k, v in zip(*np.unique(status, return_counts=True))},
                    "iters_mean": float(iters.mean()), "iters_max": int(iters.max()), "loss": loss_val},

@@ -155,6 +155,7 @@ int cave_pack(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, i
     pp.B = (int)B; pp.m_max = (int)m_max; pp.d = (int)d;
     pp.nvalid = p.nvalid; pp.ngen = p.ngen; pp.gennnz = p.gennnz; pp.nsingc = p.nsingc; pp.csr_ok = p.csr_ok;
     pp.gen4 = p.gen4; pp.ghash = p.ghash; pp.plan = (unsigned long long*)(base + L.plan);
+    pp.okey = (int*)(base + L.okey); pp.order = (int*)(base + L.order);
     e = cave::launch_plan(pp, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(CAVE_ECUDA, "plan kernel launch failed: %s", cudaGetErrorString(e));
     return CAVE_OK;
@@ -217,6 +218,7 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     sp.max_iter = opts ? opts->max_iter : 0; sp.max_ls = opts ? opts->max_linesearch : 0; sp.tol = opts ? opts->tol : 0.0;
     sp.inst_index = indexed ? opts->inst_index : nullptr;
     sp.plan = (const unsigned long long*)(pb + PL.plan);
+    sp.order = (indexed || env_int("CAVE_SOLVE_ORDER", 1) == 0) ? nullptr : (const int*)(pb + PL.order);       // the order of a dataset-wide pack does not apply to a batch
     if (solve_forced()) {
         sp.smem_bytes = env_int("CAVE_SOLVE_SMEM", 110 * 1024);
         int threads = env_int("CAVE_SOLVE_THREADS", 256);

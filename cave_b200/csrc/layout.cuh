@@ -28,8 +28,10 @@ CAVE_HD size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 //   csr_col/val[B, cap_nnz]   the general rows' non-zeros, row after row, columns ascending
 //   plan[8]     uint64 batch statistics written by the plan kernel (see PlanStats): the solve kernel's
 //               launch configuration is chosen from them on the device, without a host round trip
+//   okey[B], order[B]   per-instance cost estimate and the instances sorted by it, most expensive first: the order
+//               in which the solve kernel's persistent CTAs take them (shortens the drain at the end of the kernel)
 struct PackLayout {
-    size_t nvalid, navg, ngen, gennnz, nsingc, gen, ctype, avg, csrok, maxl1, maxl2, ghash, csr_col, csr_val, plan, total;
+    size_t nvalid, navg, ngen, gennnz, nsingc, gen, ctype, avg, csrok, maxl1, maxl2, ghash, csr_col, csr_val, plan, okey, order, total;
     int64_t dpad, cap_nnz;
 };
 
@@ -60,6 +62,8 @@ CAVE_HD PackLayout make_pack_layout(int64_t B, int64_t m_max, int64_t d) {
     L.csr_col = o; o = align_up(o + (size_t)B * (size_t)L.cap_nnz * 2, 256);
     L.csr_val = o; o = align_up(o + (size_t)B * (size_t)L.cap_nnz * 4, 256);
     L.plan = o;   o = align_up(o + 64, 256);
+    L.okey = o;   o = align_up(o + (size_t)B * 4, 256);
+    L.order = o;  o = align_up(o + (size_t)B * 4, 256);
     L.total = o;
     return L;
 }
@@ -70,6 +74,7 @@ CAVE_HD PackLayout make_pack_layout(int64_t B, int64_t m_max, int64_t d) {
 // after the scan; the plan kernel therefore reduces per-instance shared-memory footprints into PlanStats and
 // every candidate configuration is launched — the ones the statistics do not select exit at once.
 enum { PLAN_N = 0, PLAN_SUM8 = 1, PLAN_SUM4 = 2, PLAN_MAXHOT8 = 3, PLAN_MAXHOT4 = 4 };   // indices into plan[]
+constexpr int kOrderMaxBatch = 16384;     // beyond this the drain is negligible and instances are taken in index order
 struct SolveConfig { int threads, ctas_per_sm, smem_bytes; };
 constexpr int kNumSolveConfigs = 4;
 CAVE_HD SolveConfig solve_config(int i) {

@@ -644,6 +644,9 @@ __global__ void __launch_bounds__(256) plan_kernel(PlanParams p) {
         size_t hot8, work8, hot4, work4;
         instance_footprint(p.d, skip ? 0 : ngen, nv, nnz_kept, (ok & 3) == 3, dense_path, 8, &hot8, &work8);
         instance_footprint(p.d, skip ? 0 : ngen, nv, nnz_kept, (ok & 3) == 3, dense_path, 4, &hot4, &work4);
+        // cost estimate for the work queue order: non-zeros swept per iteration + the dense part of the Newton system
+        long long key = skip ? 0 : (dense_path ? (long long)ngen * p.d : nnz_kept + 16ll * nv);
+        p.okey[b] = (int)(key > 0x7fffffffll ? 0x7fffffffll : key);
         atomicAdd(p.plan + PLAN_N, 1ull);
         atomicAdd(p.plan + PLAN_SUM8, (unsigned long long)work8);
         atomicAdd(p.plan + PLAN_SUM4, (unsigned long long)work4);
@@ -652,8 +655,29 @@ __global__ void __launch_bounds__(256) plan_kernel(PlanParams p) {
     }
 }
 
+// ---- order kernel: order[rank] = b with rank(b) = number of instances that cost more (ties: lower index first).
+// Rank by counting, one warp per instance, O(B^2) comparisons in total: a few microseconds at the batch sizes
+// where the order matters; larger batches keep the index order.
+__global__ void __launch_bounds__(256) order_kernel(PlanParams p) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= p.B) return;
+    if (p.B > kOrderMaxBatch) { if (lane == 0) p.order[b] = b; return; }
+    const int mine = p.okey[b];
+    int rank = 0;
+    for (int j = lane; j < p.B; j += 32) {
+        const int k = p.okey[j];
+        rank += (k > mine) | ((k == mine) & (j < b));
+    }
+    for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+    if (lane == 0) p.order[rank] = b;
+}
+
 cudaError_t launch_plan(const PlanParams& p, cudaStream_t stream) {
     plan_kernel<<<dim3((unsigned)((p.B + 7) / 8)), dim3(256), 0, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    order_kernel<<<dim3((unsigned)((p.B + 7) / 8)), dim3(256), 0, stream>>>(p);
     return cudaGetLastError();
 }
 

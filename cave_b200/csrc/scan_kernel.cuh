@@ -32,6 +32,8 @@ struct PlanParams {
     const int4* gen4;
     const ulonglong2* ghash;
     unsigned long long* plan;   // zeroed by the caller on the same stream
+    int* okey;                  // [B] cost estimate per instance
+    int* order;                 // [B] instances by descending cost (filled by the order kernel)
 };
 cudaError_t launch_plan(const PlanParams& p, cudaStream_t stream);
 

@@ -39,6 +39,7 @@ struct SolveParams {
     // statistics select it (cfg_id < 0: forced, no check)
     int cfg_id;
     const unsigned long long* plan;
+    const int* order;      // nullable: work-queue position -> instance (most expensive first)
 };
 
 struct FinalizeParams {

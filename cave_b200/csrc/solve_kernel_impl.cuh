@@ -29,9 +29,10 @@ __global__ void __launch_bounds__(CAVE_LB_T, CAVE_LB_C) solve_kernel(SolveParams
     for (;;) {
         if (cx.tid == 0) s_b = atomicAdd(p.counter, 1);
         __syncthreads();
-        const int b = s_b;
+        const int slot_b = s_b;
         __syncthreads();
-        if (b >= p.B) break;
+        if (slot_b >= p.B) break;
+        const int b = p.order ? p.order[slot_b] : slot_b;
         const size_t q = p.inst_index ? (size_t)p.inst_index[b] : (size_t)b;     // instance of the pack / of A
         Instance in;
         in.A = p.A ? p.A + q * p.m_max * p.d : nullptr;

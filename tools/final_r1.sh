@@ -7,5 +7,5 @@ python bench.py --precision fp32 --no-cpu-baseline > gpurun_out/bench_fp32.json 
 done; done ) > gpurun_out/workloads.txt 2>&1
 python tools/sweep_check.py > gpurun_out/sweep.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1b.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_l.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"scan_rows_kernel|solve_kernel|plan_kernel|finalize" -s 21 -c 7 -o gpurun_out/prof_r1_final2 -f python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_f.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"scan_rows_kernel|solve_kernel|plan_kernel|order_kernel|finalize" -s 24 -c 8 -o gpurun_out/prof_r1_final3 -f python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_f.log 2>&1
 tail -2 gpurun_out/ncu_f.log | cut -c1-150

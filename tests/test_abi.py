@@ -57,3 +57,15 @@ def test_argument_errors_are_codes_with_messages(lib):
     assert lib.cave_pack(None, None, 8, 10, 10, None, 0, None) == -1
     assert lib.cave_forward_backward(None, None, None, 8, 10, 10, -1.0, 0, 0.2, 0, 0, 1, None, None, None, None, None,
                                      None, None, None, None, 0, None, 0, None) == -1
+
+
+def test_graft_entry_build_check_passes():
+    """The driver's "does it build" entry point: compiles (or finds fresh) the library and checks its ABI version
+    against the header."""
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    ge = importlib.import_module("__graft_entry__")
+    ge.build()

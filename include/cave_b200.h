@@ -113,7 +113,8 @@ int cave_scratch_bytes(int64_t B, int64_t m_max, int64_t d, int compute_dtype,
                        const cave_solver_opts* opts, size_t* out);
 
 /* One streaming pass over A (HBM bound): classifies every row (padding / singleton +-e_k /
- * general), accumulates the average unit normal, and writes the packed description.
+ * general), accumulates the average unit normal, and writes the packed description; two small
+ * kernels then add the solve kernel's launch-plan statistics and the cost-ordered instance list.
  * m_rows: optional int32[B] with the number of leading rows that can be non-zero per instance
  * (rows >= m_rows[b] are not read); NULL -> all m_max rows are scanned. */
 int cave_pack(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, int64_t d,

@@ -69,3 +69,24 @@ def test_graft_entry_build_check_passes():
         sys.path.insert(0, root)
     ge = importlib.import_module("__graft_entry__")
     ge.build()
+
+
+def test_launch_plan_rule_on_host(lib):
+    """cave_plan_choice applies the device's selection rule to a host copy of the plan words: the smallest configuration
+    whose shared memory holds the average working set with 5 % to spare and the largest hot set outright."""
+    from cave_b200 import _lib
+
+    def choice(n, avg8, avg4, hot8, hot4, d=1225, io=_lib.F32, comp=_lib.F64):
+        words = (ctypes.c_uint64 * 8)(n, n * avg8, n * avg4, hot8, hot4, 0, 0, 0)
+        t, c, sm = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        idx = lib.cave_plan_choice(words, d, io, comp, ctypes.byref(t), ctypes.byref(c), ctypes.byref(sm))
+        return idx, t.value, c.value, sm.value
+
+    assert choice(4096, 12000, 10000, 11000, 9000) == (0, 64, 8, 28160)            # TSP-20-sized
+    assert choice(4096, 67000, 59000, 48500, 39300)[0] == 2                           # TSP-50, float64 factor
+    assert choice(4096, 67000, 59000, 48500, 39300, comp=_lib.F32)[0] == 2            # ... float32 factor: 59 KB > 0.95 * 55 KB
+    assert choice(4096, 40000, 30000, 30000, 25000)[0] == 1
+    assert choice(4096, 40000, 30000, 60000, 25000)[0] == 2                           # one instance's hot set rules out 128 x 4
+    assert choice(16, 600000, 600000, 20000, 20000) == (3, 256, 2, 112640)            # dense Gram: widest CTA
+    assert choice(0, 0, 0, 0, 0)[0] == 3                                              # empty statistics: the default
+    assert choice(4096, 26000, 20000, 20000, 15000, d=1225, io=_lib.F64)[0] == 1      # float64 I/O adds 4 d bytes: 30.9 KB > 26.7 KB

@@ -408,15 +408,12 @@ CAVE_DEV T nw_grad_t(Ctx& cx, const NewtonWork<T, TH, TC, HOT>& W, HPtr<T, HOT> 
         T acc = (T)0;
         int e = W.rptr[row] + cx.lane;
         const int e1 = W.rptr[row + 1];
-        for (; e + 3 * Ctx::WS < e1; e += 4 * Ctx::WS) {       // four gathers in flight per lane, same order
-            const int k0 = W.rcol[e], k1 = W.rcol[e + Ctx::WS], k2 = W.rcol[e + 2 * Ctx::WS], k3 = W.rcol[e + 3 * Ctx::WS];
-            const T v0 = (T)rval[e], v1 = (T)rval[e + Ctx::WS], v2 = (T)rval[e + 2 * Ctx::WS], v3 = (T)rval[e + 3 * Ctx::WS];
+        for (; e < e1; e += 4 * Ctx::WS) {                     // guarded: up to four gathers in flight per lane, same order
+            const bool p1 = e + Ctx::WS < e1, p2 = e + 2 * Ctx::WS < e1, p3 = e + 3 * Ctx::WS < e1;
+            const int k0 = W.rcol[e], k1 = p1 ? (int)W.rcol[e + Ctx::WS] : 0, k2 = p2 ? (int)W.rcol[e + 2 * Ctx::WS] : 0, k3 = p3 ? (int)W.rcol[e + 3 * Ctx::WS] : 0;
+            const T v0 = (T)rval[e], v1 = p1 ? (T)rval[e + Ctx::WS] : (T)0, v2 = p2 ? (T)rval[e + 2 * Ctx::WS] : (T)0, v3 = p3 ? (T)rval[e + 3 * Ctx::WS] : (T)0;
             const T r0 = r[k0], r1 = r[k1], r2 = r[k2], r3 = r[k3];          // r holds psi(r) already (nw_eval2)
             acc += v0 * r0; acc += v1 * r1; acc += v2 * r2; acc += v3 * r3;
-        }
-        for (; e < e1; e += Ctx::WS) {
-            int k = W.rcol[e];
-            acc += (T)rval[e] * (T)r[k];
         }
         acc = cx.warp_sum(acc);
         const T gv = -acc, nv_ = nu[v];

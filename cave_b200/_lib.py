@@ -12,16 +12,18 @@ CAVE_OK = 0
 MODE_EXACT, MODE_INNER, MODE_HEURISTIC = 0, 1, 2
 REDUCE = {"mean": 0, "sum": 1, "none": 2}
 F32, F64 = 0, 1
-ST_CONVERGED, ST_ITER_CAP, ST_STALLED, ST_NOSPACE, ST_SKIPPED, ST_BADINPUT, ST_PATH_LH = 0, 1, 2, 3, 4, 5, 0x100
+ST_CONVERGED, ST_ITER_CAP, ST_STALLED, ST_NOSPACE, ST_SKIPPED, ST_BADINPUT, ST_PATH_LH, ST_PATH_GRAM = 0, 1, 2, 3, 4, 5, 0x100, 0x200
 
 EXPORTS = ("cave_abi_version", "cave_last_error", "cave_get_limits", "cave_pack_bytes",
-           "cave_scratch_bytes", "cave_pack", "cave_forward_backward", "cave_plan_offset", "cave_plan_choice")
+           "cave_scratch_bytes", "cave_pack", "cave_forward_backward", "cave_plan_offset", "cave_plan_choice",
+           "cave_dense_gram")
 
 
 class SolverOpts(ctypes.Structure):
     _fields_ = [("max_iter", ctypes.c_int32), ("max_linesearch", ctypes.c_int32), ("tol", ctypes.c_double),
                 ("cap_rows", ctypes.c_int64), ("cap_nnz", ctypes.c_int64), ("warm_pack", ctypes.c_int32),
-                ("reserved", ctypes.c_int32), ("inst_index", ctypes.c_void_p), ("n_packed", ctypes.c_int64)]
+                ("dense_mode", ctypes.c_int32), ("inst_index", ctypes.c_void_p), ("n_packed", ctypes.c_int64),
+                ("dense_slots", ctypes.c_int64)]
 
 
 class Limits(ctypes.Structure):
@@ -56,11 +58,12 @@ def load() -> ctypes.CDLL:
     lib.cave_forward_backward.argtypes = [P, P, P, I64, I64, I64, F, I32, F, I32, I32, I32,
                                           ctypes.POINTER(SolverOpts), P, P, P, P, P, P, P,
                                           P, ctypes.c_size_t, P, ctypes.c_size_t, P]
+    lib.cave_dense_gram.argtypes = [P, I64, I64, I64, ctypes.POINTER(SolverOpts), P, P, P, ctypes.c_size_t, P, ctypes.c_size_t, P]
     lib.cave_plan_offset.argtypes = [I64, I64, I64, SZP]
     IP = ctypes.POINTER(ctypes.c_int)
     lib.cave_plan_choice.argtypes = [ctypes.POINTER(ctypes.c_uint64), I64, I32, I32, IP, IP, IP]
     for name in ("cave_get_limits", "cave_pack_bytes", "cave_scratch_bytes", "cave_pack", "cave_forward_backward",
-                 "cave_plan_offset", "cave_plan_choice"):
+                 "cave_plan_offset", "cave_plan_choice", "cave_dense_gram"):
         getattr(lib, name).restype = I32
     _lib = lib
     return lib

@@ -23,7 +23,8 @@ from ._pyepo_compat import EPO, optModule
 from .qpsolver import CavePack, cave_forward_backward, project_cuda
 
 _REFERENCE_SOLVERS = ("apgd", "clarabel", "nnls")
-_KERNEL_KWARGS = ("precision", "max_iter", "max_linesearch", "tol", "cap_rows", "cap_nnz", "device", "pack", "m_rows", "index")
+_KERNEL_KWARGS = ("precision", "max_iter", "max_linesearch", "tol", "cap_rows", "cap_nnz", "device", "pack", "m_rows", "index",
+                  "dense", "dense_slots")
 
 
 class _CaveCudaFunction(torch.autograd.Function):

@@ -11,6 +11,7 @@
 #include "layout.cuh"
 #include "scan_kernel.cuh"
 #include "solve_kernel.cuh"
+#include "dense.cuh"
 
 namespace {
 
@@ -35,14 +36,15 @@ int env_int(const char* name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-int sm_count() {
-    static int cached = 0;
-    if (cached > 0) return cached;
+int sm_count() {                    // of the CURRENT device (cached per device: a process may drive several GPUs)
+    static int cached[64] = {0};
     int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
-        cached = n;
-        return n;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+        if (cached[dev] > 0) return cached[dev];
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
+            cached[dev] = n;
+            return n;
+        }
     }
     (void)cudaGetLastError();
     return 148;                     // B200; used only for sizing when no device is visible
@@ -77,6 +79,26 @@ void resolve_caps(const cave_solver_opts* o, int64_t m_max, int64_t d, int64_t* 
     int64_t z = (o && o->cap_nnz > 0) ? o->cap_nnz : r * d;
     if (z > r * d) z = r * d;
     *cap_rows = r; *cap_nnz = z;
+}
+
+// ---- dense (tensor-core Gram) path: host-side gate and workspace sizing
+bool dense_enabled(const cave_solver_opts* o, const float* A, int64_t m_max, int64_t d, int mode) {
+    const int dm = o ? o->dense_mode : 0;
+    if (dm < 0 || !A || mode == CAVE_MODE_HEURISTIC) return false;
+    if (m_max < cave::kDenseMinRows || cave::dense_m_pad(m_max) > 2048) return false;
+    return dm > 0 || m_max <= d;      // auto: structured models (one bound row per variable) always have m > d
+}
+
+int64_t dense_slots(const cave_solver_opts* o, int64_t B, int64_t m_max, int64_t d) {
+    int64_t n;
+    if (o && o->dense_slots > 0) n = o->dense_slots;
+    else {
+        const int64_t sms = sm_count();
+        const int64_t by_budget = (int64_t)(((size_t)12 << 30) / cave::dense_slot_bytes(m_max, d));
+        n = 4 * sms < by_budget ? 4 * sms : by_budget;
+        if (n < sms) n = sms;
+    }
+    return n < B ? n : B;
 }
 
 }  // namespace
@@ -126,7 +148,12 @@ int cave_scratch_bytes(int64_t B, int64_t m_max, int64_t d, int compute_dtype, c
     if (compute_dtype != CAVE_F32 && compute_dtype != CAVE_F64) return fail(CAVE_EINVAL, "bad compute_dtype %d", compute_dtype);
     int64_t cr, cz;
     resolve_caps(opts, m_max, d, &cr, &cz);
-    *out = cave::make_scratch_layout(B, d, cr, cz, 8, solver_slots(B, cave::solver_slot_bytes(d, cr, cz, 8))).total;
+    size_t total = cave::make_scratch_layout(B, d, cr, cz, 8, solver_slots(B, cave::solver_slot_bytes(d, cr, cz, 8))).total;
+    // mode and A are not known here: sized for the case that the call takes the dense path
+    static const float kSomeA = 0.f;
+    if (dense_enabled(opts, &kSomeA, m_max, d, CAVE_MODE_EXACT))
+        total = cave::make_dense_layout(B, m_max, d, dense_slots(opts, B, m_max, d), total).total;
+    *out = total;
     return CAVE_OK;
 }
 
@@ -189,7 +216,12 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     const size_t T = 8;   // state vectors are double in both modes; sized for the f64 factor
     const int64_t n_slots = solver_slots(B, cave::solver_slot_bytes(d, cr, cz, T));
     const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, cr, cz, T, n_slots);
-    if (scratch_bytes < SL.total) return fail(CAVE_ENOSPC, "scratch buffer has %zu bytes, %zu needed", scratch_bytes, SL.total);
+    const bool dense = dense_enabled(opts, A, m_max, d, mode);
+    cave::DenseLayout DL;
+    memset(&DL, 0, sizeof(DL));
+    if (dense) DL = cave::make_dense_layout(B, m_max, d, dense_slots(opts, B, m_max, d), SL.total);
+    const size_t need = dense ? DL.total : SL.total;
+    if (scratch_bytes < need) return fail(CAVE_ENOSPC, "scratch buffer has %zu bytes, %zu needed", scratch_bytes, need);
 
     cudaStream_t st = (cudaStream_t)stream;
     if (!(opts && opts->warm_pack)) {
@@ -219,6 +251,36 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     sp.inst_index = indexed ? opts->inst_index : nullptr;
     sp.plan = (const unsigned long long*)(pb + PL.plan);
     sp.order = (indexed || env_int("CAVE_SOLVE_ORDER", 1) == 0) ? nullptr : (const int*)(pb + PL.order);       // the order of a dataset-wide pack does not apply to a batch
+    sp.n_packed = Bpack;
+    sp.dense_flag = nullptr;
+    if (dense) {
+        // Dense regime first: instance list, then per round of n_slots instances the TF32 split, the tensor-core Gram and
+        // the Gram-space solve.  Everything is decided on the device; a batch without dense instances costs the list
+        // kernel and 3 x rounds launches that return at once.  Instances the Gram-space solver hands back are taken by
+        // the general solve kernel below (Lawson-Hanson).
+        cave::DenseParams dp;
+        memset(&dp, 0, sizeof(dp));
+        dp.A = A; dp.pred = pred; dp.B = (int)B; dp.m_max = (int)m_max; dp.d = (int)d;
+        dp.inst_index = sp.inst_index; dp.nvalid = sp.nvalid; dp.ngen = sp.ngen; dp.nsingc = sp.nsingc; dp.gen = sp.gen;
+        dp.ctype = sp.ctype; dp.avg = sp.avg; dp.dpad = PL.dpad;
+        dp.ws = sb; dp.L = DL; dp.force = (opts && opts->dense_mode > 0) ? 1 : 0;
+        dp.grad = grad; dp.proj = proj; dp.loss64 = sp.loss64; dp.rnorm64 = sp.rnorm64; dp.status = sp.status; dp.iters = sp.iters;
+        dp.mode = mode; dp.inner_ratio = inner_ratio; dp.sign = sign; dp.gscale = sp.gscale;
+        dp.max_iter = 0; dp.max_ls = sp.max_ls; dp.tol = sp.tol; dp.io_f32 = io_dtype == CAVE_F32; dp.nk = (int)(DL.d_pad / 32);
+        ce = cave::launch_dense_list(dp, st);
+        if (ce != cudaSuccess) return fail(CAVE_ECUDA, "dense list kernel launch failed: %s", cudaGetErrorString(ce));
+        const int64_t rounds = (B + DL.n_slots - 1) / DL.n_slots;
+        for (int64_t r = 0; r < rounds; ++r) {
+            dp.round = (int)r;
+            ce = cave::launch_dense_prep(dp, st);
+            if (ce != cudaSuccess) return fail(CAVE_ECUDA, "dense prep kernel launch failed: %s", cudaGetErrorString(ce));
+            ce = cave::launch_dense_gram(dp, st);
+            if (ce != cudaSuccess) return fail(CAVE_ECUDA, "dense Gram kernel launch failed: %s (%s)", cudaGetErrorString(ce), cave::dense_last_error());
+            ce = cave::launch_dense_solve(dp, st);
+            if (ce != cudaSuccess) return fail(CAVE_ECUDA, "dense solve kernel launch failed: %s", cudaGetErrorString(ce));
+        }
+        sp.dense_flag = (const int*)(sb + DL.flag);
+    }
     if (solve_forced()) {
         sp.smem_bytes = env_int("CAVE_SOLVE_SMEM", 110 * 1024);
         int threads = env_int("CAVE_SOLVE_THREADS", 256);
@@ -248,6 +310,53 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     fp.loss = loss; fp.loss_i = loss_i; fp.rnorm = rnorm; fp.status_out = status; fp.iters_out = iters;
     ce = cave::launch_finalize(fp, io_dtype == CAVE_F32, st);
     if (ce != cudaSuccess) return fail(CAVE_ECUDA, "finalize kernel launch failed: %s", cudaGetErrorString(ce));
+    return CAVE_OK;
+}
+
+int cave_dense_gram(const float* A, int64_t B, int64_t m_max, int64_t d, const cave_solver_opts* opts, float* G_out,
+                    int32_t* n_dense_out, void* pack, size_t pack_bytes, void* scratch, size_t scratch_bytes, void* stream) {
+    if (!A || !G_out || !pack || !scratch) return fail(CAVE_EINVAL, "A, G_out, pack, scratch must not be null");
+    if (int e = check_shape(B, m_max, d)) return e;
+    cave_solver_opts o;
+    memset(&o, 0, sizeof(o));
+    if (opts) o = *opts;
+    o.dense_mode = 1;
+    if (!dense_enabled(&o, A, m_max, d, CAVE_MODE_EXACT)) return fail(CAVE_ELIMIT, "shape outside the dense path (128 <= m_max <= 2048)");
+    if (((uintptr_t)scratch & 255) != 0 || ((uintptr_t)pack & 255) != 0) return fail(CAVE_EINVAL, "pack and scratch must be 256-byte aligned");
+    if (!o.warm_pack) { if (int e = cave_pack(A, nullptr, B, m_max, d, pack, pack_bytes, stream)) return e; }
+    const cave::PackLayout PL = cave::make_pack_layout(B, m_max, d);
+    if (pack_bytes < PL.total) return fail(CAVE_ENOSPC, "pack buffer has %zu bytes, %zu needed", pack_bytes, PL.total);
+    int64_t cr, cz;
+    resolve_caps(&o, m_max, d, &cr, &cz);
+    const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, cr, cz, 8, solver_slots(B, cave::solver_slot_bytes(d, cr, cz, 8)));
+    const cave::DenseLayout DL = cave::make_dense_layout(B, m_max, d, dense_slots(&o, B, m_max, d), SL.total);
+    if (scratch_bytes < DL.total) return fail(CAVE_ENOSPC, "scratch buffer has %zu bytes, %zu needed", scratch_bytes, DL.total);
+    char* pb = (char*)pack;
+    char* sb = (char*)scratch;
+    cudaStream_t st = (cudaStream_t)stream;
+    cave::DenseParams dp;
+    memset(&dp, 0, sizeof(dp));
+    static const float kZero = 0.f;
+    dp.A = A; dp.pred = &kZero; dp.B = (int)B; dp.m_max = (int)m_max; dp.d = (int)d;
+    dp.nvalid = (const int*)(pb + PL.nvalid); dp.ngen = (const int*)(pb + PL.ngen); dp.nsingc = (const int*)(pb + PL.nsingc);
+    dp.gen = (const int4*)(pb + PL.gen); dp.ctype = (const unsigned char*)(pb + PL.ctype); dp.avg = (const float*)(pb + PL.avg);
+    dp.dpad = PL.dpad; dp.ws = sb; dp.L = DL; dp.force = 1; dp.sign = 0.0; dp.io_f32 = 1; dp.nk = (int)(DL.d_pad / 32);
+    // prep reads pred[b * d + k] for the right-hand side b = A c: point it at A's first rows (any finite data will do)
+    dp.pred = A;
+    cudaError_t ce = cave::launch_dense_list(dp, st);
+    if (ce != cudaSuccess) return fail(CAVE_ECUDA, "dense list kernel launch failed: %s", cudaGetErrorString(ce));
+    dp.round = 0;
+    ce = cave::launch_dense_prep(dp, st);
+    if (ce != cudaSuccess) return fail(CAVE_ECUDA, "dense prep kernel launch failed: %s", cudaGetErrorString(ce));
+    ce = cave::launch_dense_gram(dp, st);
+    if (ce != cudaSuccess) return fail(CAVE_ECUDA, "dense Gram kernel launch failed: %s (%s)", cudaGetErrorString(ce), cave::dense_last_error());
+    const int64_t n = DL.n_slots < B ? DL.n_slots : B;
+    ce = cudaMemcpyAsync(G_out, sb + DL.G, (size_t)n * DL.m_pad * DL.m_pad * 4, cudaMemcpyDeviceToDevice, st);
+    if (ce != cudaSuccess) return fail(CAVE_ECUDA, "copy of G failed: %s", cudaGetErrorString(ce));
+    if (n_dense_out) {
+        ce = cudaMemcpyAsync(n_dense_out, sb + DL.ctrl, 4, cudaMemcpyDeviceToDevice, st);
+        if (ce != cudaSuccess) return fail(CAVE_ECUDA, "copy of the dense count failed: %s", cudaGetErrorString(ce));
+    }
     return CAVE_OK;
 }
 

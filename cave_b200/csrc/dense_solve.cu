@@ -1,0 +1,615 @@
+// Dense regime, kernel 4: one CTA per instance solves  min_{lam >= 0} 1/2 ||A^T lam - c||^2  in Gram space.
+//
+// Phase 1 (Gram space, reads only G~ and b): Bertsekas' two-metric projected Newton on q(lam) = 1/2 lam^T G~ lam - b^T lam.
+//   Free set F = variables that are not epsilon-binding; Newton system (G~_FF + reg I) x = g_F by a blocked left-looking
+//   float32 Cholesky in the instance's global workspace (register-tiled 8 x 8 FFMA kernel fed from shared memory, 64-column
+//   block columns, 32 x 32 diagonal blocks factored in registers by one warp), Armijo search along the projection arc.
+//   The gradient of the accepted trial point is the G~ matvec that evaluated it.  Stops at 1e-6 of the KKT scale: G~
+//   (3xTF32) is not more accurate than that.
+// Phase 2 (anchors the result to A, float64): the same iteration with the TRUE gradient g = A (A^T lam - c), i.e. two passes
+//   over the rows of A per step, and the Cholesky factor of phase 1 as the metric (refactored only if F changes).  Each
+//   step contracts the error by about cond(G_FF) * 1e-6, so one or two steps reach the float64 KKT tolerance that the
+//   Lawson-Hanson path and scipy.optimize.nnls (src/cave.py:307) reach.
+// An instance that does not converge (e.g. m > d with the cone the whole space: G singular, the solution not unique)
+// is handed back: its flag is cleared and the Lawson-Hanson path of the general solve kernel, launched afterwards, takes it.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "dense.cuh"
+#include "solver_core.cuh"
+
+namespace cave {
+
+constexpr int kDT = 512;            // threads per CTA
+constexpr int kRC = 512;            // rows per chunk of the block-column update (one row per thread when staging)
+constexpr int kNB = 64;             // block-column width
+constexpr int kKS = 16;             // k-slab of the update
+
+struct DenseSmem {
+    double *lam, *lamt, *g, *gt, *dir, *bb;
+    int *fl, *flp;
+    int *arow, *sup;                // row of A behind every variable; support list of the point being evaluated
+    float *As, *Bs, *D, *Dt, *invd;
+    float *xs;                      // [m_pad] float32 right-hand side / solution of the triangular solves
+};
+
+__host__ __device__ inline size_t dense_solve_smem(int64_t m_pad) {
+    size_t o = 0;
+    o += 6 * (size_t)m_pad * 8;                 // lam lamt g gt dir bb
+    o += 4 * (size_t)m_pad * 4;                 // free lists, arow, sup
+    o += (size_t)m_pad * 4;                     // xs
+    o += (size_t)kKS * kRC * 4 + (size_t)kKS * kNB * 4;     // As, Bs
+    o += (size_t)kNB * (kNB + 1) * 4 + (size_t)kNB * kNB * 4 + kNB * 4; // D, Dt, invd
+    return o + 256;
+}
+
+// ---- 32 x 32 Cholesky by one warp: lane i holds row i of the lower triangle in registers.  On return lane i holds row i
+// of L (diagonal included); pivots are floored.
+__device__ __forceinline__ void chol32_warp(float (&a)[32], int lane, float floor_) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        const float piv = __shfl_sync(0xffffffffu, a[c], c);
+        const float l = sqrtf(piv > floor_ ? piv : floor_);
+        const float inv = 1.0f / l;
+        const float mine = lane == c ? l : a[c] * inv;
+        a[c] = mine;
+#pragma unroll
+        for (int j = c + 1; j < 32; ++j) {
+            const float ljc = __shfl_sync(0xffffffffu, mine, j);
+            a[j] = fmaf(-mine, ljc, a[j]);          // rows i >= j use it; others hold garbage above the diagonal
+        }
+    }
+}
+
+// Factor the kNB x kNB diagonal block held in D (row stride kNB + 1, lower triangle valid) in place; nb valid rows.
+// All threads call; ends with a barrier.  invd[c] = 1 / L[c][c].
+__device__ void factor_diag(float* D, float* invd, int nb, float floor_, int tid) {
+    constexpr int LD = kNB + 1;
+    const int lane = tid & 31, warp = tid >> 5;
+    // rows / columns >= nb: identity, so the 64-wide code below needs no bounds
+    for (int t = tid; t < kNB * kNB; t += kDT) {
+        const int i = t / kNB, j = t - i * kNB;
+        if (i >= nb || j >= nb) D[i * LD + j] = i == j ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+    if (warp == 0) {                                    // D11
+        float a[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = j <= lane ? D[lane * LD + j] : 0.0f;
+        chol32_warp(a, lane, floor_);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j <= lane) D[lane * LD + j] = a[j];
+    }
+    __syncthreads();
+    // invd of the first block: lane holds a[lane] only by dynamic index; recompute from memory
+    if (tid < 32) invd[tid] = 1.0f / D[tid * LD + tid];
+    __syncthreads();
+    if (tid < 32) {                                     // D21 <- D21 L11^-T : one thread per row 32 + tid
+        float x[32];
+        const int r = 32 + tid;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = D[r * LD + j];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            float s = x[c];
+#pragma unroll
+            for (int q = 0; q < c; ++q) s = fmaf(-x[q], D[c * LD + q], s);
+            x[c] = s * invd[c];
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) D[r * LD + j] = x[j];
+    }
+    __syncthreads();
+    for (int t = tid; t < 32 * 32; t += kDT) {          // D22 -= D21 D21^T (lower triangle)
+        const int i = t >> 5, j = t & 31;
+        if (j <= i) {
+            float s = D[(32 + i) * LD + 32 + j];
+#pragma unroll 8
+            for (int q = 0; q < 32; ++q) s = fmaf(-D[(32 + i) * LD + q], D[(32 + j) * LD + q], s);
+            D[(32 + i) * LD + 32 + j] = s;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {                                    // D22
+        float a[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = j <= lane ? D[(32 + lane) * LD + 32 + j] : 0.0f;
+        chol32_warp(a, lane, floor_);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j <= lane) D[(32 + lane) * LD + 32 + j] = a[j];
+    }
+    __syncthreads();
+    if (tid < 32) invd[32 + tid] = 1.0f / D[(32 + tid) * LD + 32 + tid];
+    __syncthreads();
+}
+
+// Blocked left-looking Cholesky of the nf x nf lower triangle in W (row stride ldw): W <- L.
+__device__ void chol_blocked(float* __restrict__ W, int ldw, int nf, float floor_, const DenseSmem& S, int tid) {
+    constexpr int LD = kNB + 1;
+    const int tr = tid & 63, tcg = tid >> 6;            // micro-tile: rows tr*8.., columns tcg*8..
+    for (int j0 = 0; j0 < nf; j0 += kNB) {
+        const int nb = nf - j0 < kNB ? nf - j0 : kNB;
+        for (int r0 = j0; r0 < nf; r0 += kRC) {
+            if (j0 > 0) {
+                // ---- acc = sum_{p < j0} L[r0 + ., p] L[j0 + ., p]^T  for the chunk's 512 rows x 64 columns
+                float acc[8][8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+                const int myrow = r0 + tid < nf ? r0 + tid : nf - 1;            // staging: one row per thread (clamped)
+                const int mybrow = j0 + (tid & 63) < nf ? j0 + (tid & 63) : nf - 1;
+                const float* arow = W + (size_t)myrow * ldw;
+                const float* brow = W + (size_t)mybrow * ldw;
+                float4 pa[4], pb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    pa[u] = *reinterpret_cast<const float4*>(arow + u * 4);
+                    pb[u] = tid < 64 ? *reinterpret_cast<const float4*>(brow + u * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                for (int p0 = 0; p0 < j0; p0 += kKS) {
+                    __syncthreads();                    // previous slab consumed
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        S.As[(u * 4 + 0) * kRC + tid] = pa[u].x; S.As[(u * 4 + 1) * kRC + tid] = pa[u].y;
+                        S.As[(u * 4 + 2) * kRC + tid] = pa[u].z; S.As[(u * 4 + 3) * kRC + tid] = pa[u].w;
+                        if (tid < 64) {
+                            S.Bs[(u * 4 + 0) * kNB + tid] = pb[u].x; S.Bs[(u * 4 + 1) * kNB + tid] = pb[u].y;
+                            S.Bs[(u * 4 + 2) * kNB + tid] = pb[u].z; S.Bs[(u * 4 + 3) * kNB + tid] = pb[u].w;
+                        }
+                    }
+                    __syncthreads();
+                    if (p0 + kKS < j0) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            pa[u] = *reinterpret_cast<const float4*>(arow + p0 + kKS + u * 4);
+                            if (tid < 64) pb[u] = *reinterpret_cast<const float4*>(brow + p0 + kKS + u * 4);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kKS; ++k) {
+                        const float4 a0 = *reinterpret_cast<const float4*>(S.As + k * kRC + tr * 8);
+                        const float4 a1 = *reinterpret_cast<const float4*>(S.As + k * kRC + tr * 8 + 4);
+                        const float4 b0 = *reinterpret_cast<const float4*>(S.Bs + k * kNB + tcg * 8);
+                        const float4 b1 = *reinterpret_cast<const float4*>(S.Bs + k * kNB + tcg * 8 + 4);
+                        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                    }
+                }
+                // ---- W[r, j0 + c] -= acc
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = r0 + tr * 8 + i;
+                    if (r < nf) {
+                        float* w = W + (size_t)r * ldw + j0 + tcg * 8;
+                        float4 w0 = *reinterpret_cast<float4*>(w), w1 = *reinterpret_cast<float4*>(w + 4);
+                        w0.x -= acc[i][0]; w0.y -= acc[i][1]; w0.z -= acc[i][2]; w0.w -= acc[i][3];
+                        w1.x -= acc[i][4]; w1.y -= acc[i][5]; w1.z -= acc[i][6]; w1.w -= acc[i][7];
+                        *reinterpret_cast<float4*>(w) = w0; *reinterpret_cast<float4*>(w + 4) = w1;
+                    }
+                }
+            }
+            __syncthreads();
+            if (r0 == j0) {
+                // ---- diagonal block: factor in shared memory, write L_jj back; Dt = aligned copy for the row solves
+                for (int t = tid; t < kNB * kNB; t += kDT) {
+                    const int i = t / kNB, j = t - i * kNB;
+                    S.D[i * LD + j] = (i < nb && j <= i) ? W[(size_t)(j0 + i) * ldw + j0 + j] : 0.0f;
+                }
+                __syncthreads();
+                factor_diag(S.D, S.invd, nb, floor_, tid);
+                for (int t = tid; t < kNB * kNB; t += kDT) {
+                    const int i = t / kNB, j = t - i * kNB;
+                    const float v = S.D[i * LD + j];
+                    S.Dt[t] = j < i ? v : 0.0f;
+                    if (i < nb && j <= i) W[(size_t)(j0 + i) * ldw + j0 + j] = v;
+                }
+                __syncthreads();
+            }
+            // ---- rows below the diagonal block: x <- x L_jj^-T, one row per thread
+            {
+                const int r = r0 + tid;
+                if (r >= j0 + kNB && r < nf) {
+                    float* w = W + (size_t)r * ldw + j0;
+                    float x[kNB];
+#pragma unroll
+                    for (int u = 0; u < kNB / 4; ++u) {
+                        const float4 v = *reinterpret_cast<const float4*>(w + u * 4);
+                        x[u * 4] = v.x; x[u * 4 + 1] = v.y; x[u * 4 + 2] = v.z; x[u * 4 + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int c = 0; c < kNB; ++c) {
+                        float s = x[c];
+#pragma unroll
+                        for (int q4 = 0; q4 < (c + 3) / 4; ++q4) {      // Dt is zero on and above the diagonal
+                            const float4 l4 = *reinterpret_cast<const float4*>(S.Dt + c * kNB + q4 * 4);
+                            s = fmaf(-x[q4 * 4], l4.x, s); s = fmaf(-x[q4 * 4 + 1], l4.y, s);
+                            s = fmaf(-x[q4 * 4 + 2], l4.z, s); s = fmaf(-x[q4 * 4 + 3], l4.w, s);
+                        }
+                        x[c] = s * S.invd[c];
+                    }
+#pragma unroll
+                    for (int u = 0; u < kNB / 4; ++u)
+                        *reinterpret_cast<float4*>(w + u * 4) = make_float4(x[u * 4], x[u * 4 + 1], x[u * 4 + 2], x[u * 4 + 3]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Solve L L^T x = rhs for the factor in W; rhs in S.xs (float32, length nf), solution returned there.
+__device__ void chol_solve_blocked(const float* __restrict__ W, int ldw, int nf, const DenseSmem& S, int tid) {
+    constexpr int LD = kNB + 1;
+    const int lane = tid & 31, warp = tid >> 5;
+    float* x = S.xs;
+    // forward: L y = rhs
+    for (int j0 = 0; j0 < nf; j0 += kNB) {
+        const int nb = nf - j0 < kNB ? nf - j0 : kNB;
+        for (int t = tid; t < kNB * kNB; t += kDT) {
+            const int i = t / kNB, j = t - i * kNB;
+            S.D[i * LD + j] = (i < nb && j <= i) ? W[(size_t)(j0 + i) * ldw + j0 + j] : (i == j ? 1.0f : 0.0f);
+        }
+        for (int i = warp; i < nb; i += kDT / 32) {         // s_i = sum_{p < j0} L[i][p] y[p]
+            const float* row = W + (size_t)(j0 + i) * ldw;
+            float s = 0.0f;
+            for (int q = lane * 4; q < j0; q += 128) {
+                const float4 l4 = *reinterpret_cast<const float4*>(row + q);
+                s = fmaf(l4.x, x[q], s); s = fmaf(l4.y, x[q + 1], s); s = fmaf(l4.z, x[q + 2], s); s = fmaf(l4.w, x[q + 3], s);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) S.invd[i] = s;
+        }
+        __syncthreads();
+        if (warp == 0) {                                    // 64-step substitution, two rows per lane
+            float t0 = lane < nb ? x[j0 + lane] - S.invd[lane] : 0.0f;
+            float t1 = lane + 32 < nb ? x[j0 + lane + 32] - S.invd[lane + 32] : 0.0f;
+            const float i0 = 1.0f / S.D[lane * LD + lane], i1 = 1.0f / S.D[(lane + 32) * LD + lane + 32];
+            for (int c = 0; c < nb; ++c) {
+                const float yc = __shfl_sync(0xffffffffu, c < 32 ? t0 * i0 : t1 * i1, c & 31);
+                if (lane == (c & 31)) { if (c < 32) t0 = yc; else t1 = yc; }
+                if (lane > c) t0 = fmaf(-S.D[lane * LD + c], yc, t0);
+                if (lane + 32 > c) t1 = fmaf(-S.D[(lane + 32) * LD + c], yc, t1);
+            }
+            if (lane < nb) x[j0 + lane] = t0;
+            if (lane + 32 < nb) x[j0 + lane + 32] = t1;
+        }
+        __syncthreads();
+    }
+    // backward: L^T x = y
+    for (int j0 = ((nf - 1) / kNB) * kNB; j0 >= 0; j0 -= kNB) {
+        const int nb = nf - j0 < kNB ? nf - j0 : kNB;
+        for (int t = tid; t < kNB * kNB; t += kDT) {
+            const int i = t / kNB, j = t - i * kNB;
+            S.D[i * LD + j] = (i < nb && j <= i) ? W[(size_t)(j0 + i) * ldw + j0 + j] : (i == j ? 1.0f : 0.0f);
+        }
+        // s_c = sum_{i >= j0 + nb} L[i][j0 + c] x[i]: warps over rows i, lanes over the block's columns (two each)
+        float s0 = 0.0f, s1 = 0.0f;
+        for (int i = j0 + nb + warp; i < nf; i += kDT / 32) {
+            const float xi = x[i];
+            const float* row = W + (size_t)i * ldw + j0;
+            s0 = fmaf(row[lane], xi, s0);
+            s1 = fmaf(row[lane + 32], xi, s1);
+        }
+        S.As[warp * kNB + lane] = s0; S.As[warp * kNB + lane + 32] = s1;
+        __syncthreads();
+        if (warp == 0) {
+            float a0 = 0.0f, a1 = 0.0f;
+            for (int w = 0; w < kDT / 32; ++w) { a0 += S.As[w * kNB + lane]; a1 += S.As[w * kNB + lane + 32]; }
+            float t0 = lane < nb ? x[j0 + lane] - a0 : 0.0f;
+            float t1 = lane + 32 < nb ? x[j0 + lane + 32] - a1 : 0.0f;
+            const float i0 = 1.0f / S.D[lane * LD + lane], i1 = 1.0f / S.D[(lane + 32) * LD + lane + 32];
+            for (int c = nb - 1; c >= 0; --c) {
+                const float xc = __shfl_sync(0xffffffffu, c < 32 ? t0 * i0 : t1 * i1, c & 31);
+                if (lane == (c & 31)) { if (c < 32) t0 = xc; else t1 = xc; }
+                if (lane < c) t0 = fmaf(-S.D[c * LD + lane], xc, t0);
+                if (lane + 32 < c) t1 = fmaf(-S.D[c * LD + lane + 32], xc, t1);
+            }
+            if (lane < nb) x[j0 + lane] = t0;
+            if (lane + 32 < nb) x[j0 + lane + 32] = t1;
+        }
+        __syncthreads();
+    }
+}
+
+// gt = G lamt - bb over all m rows (one warp per row, float64 accumulation); returns lamt^T gt and bb^T lamt
+__device__ void gram_matvec(const float* __restrict__ G, int ldg, int m, const double* lamt, const double* bb, double* gt,
+                            Ctx& cx, double& lg, double& lb) {
+    double a_lg = 0.0, a_lb = 0.0;
+    for (int v = cx.warp; v < m; v += cx.nwarp) {
+        const float* row = G + (size_t)v * ldg;
+        double s = 0.0;
+        for (int j = cx.lane * 4; j < m; j += 128) {        // columns up to the next multiple of 128 are zero in G and in lamt
+            const float4 g4 = *reinterpret_cast<const float4*>(row + j);
+            s += (double)g4.x * lamt[j] + (double)g4.y * lamt[j + 1] + (double)g4.z * lamt[j + 2] + (double)g4.w * lamt[j + 3];
+        }
+        s = cx.warp_sum(s);
+        const double gv = s - bb[v];
+        if (cx.lane == 0) { gt[v] = gv; a_lg += lamt[v] * gv; a_lb += bb[v] * lamt[v]; }
+    }
+    cx.block_sum2(a_lg, a_lb);
+    lg = a_lg; lb = a_lb;
+}
+
+// rout = c - A^T x through the rows of A (float64), returns ||rout||^2.  The support of x is compacted first so that the
+// column loop has no branch; four rows in flight per thread.
+template <class TIO>
+__device__ double true_residual(const float* __restrict__ Ainst, int d, int m, const double* x, const TIO* c, double* rout,
+                                const DenseSmem& S, Ctx& cx, int* s_cnt) {
+    if (cx.warp == 0) {
+        int cnt = 0;
+        for (int v0 = 0; v0 < m; v0 += 32) {
+            const int v = v0 + cx.lane;
+            const bool on = v < m && x[v] != 0.0;
+            const unsigned mk = __ballot_sync(0xffffffffu, on);
+            if (on) S.sup[cnt + __popc(mk & ((1u << cx.lane) - 1u))] = v;
+            cnt += __popc(mk);
+        }
+        if (cx.lane == 0) *s_cnt = cnt;
+    }
+    __syncthreads();
+    const int ns = *s_cnt;
+    double ff = 0.0;
+    for (int k = cx.tid; k < d; k += cx.nthr) {
+        double acc = (double)c[k];
+        int i = 0;
+        for (; i + 4 <= ns; i += 4) {
+            const int v0 = S.sup[i], v1 = S.sup[i + 1], v2 = S.sup[i + 2], v3 = S.sup[i + 3];
+            const float a0 = __ldg(Ainst + (size_t)S.arow[v0] * d + k), a1 = __ldg(Ainst + (size_t)S.arow[v1] * d + k);
+            const float a2 = __ldg(Ainst + (size_t)S.arow[v2] * d + k), a3 = __ldg(Ainst + (size_t)S.arow[v3] * d + k);
+            acc -= x[v0] * (double)a0; acc -= x[v1] * (double)a1; acc -= x[v2] * (double)a2; acc -= x[v3] * (double)a3;
+        }
+        for (; i < ns; ++i) { const int v = S.sup[i]; acc -= x[v] * (double)__ldg(Ainst + (size_t)S.arow[v] * d + k); }
+        rout[k] = acc; ff += acc * acc;
+    }
+    return cx.block_sum(ff);        // (barriers inside: rout is visible afterwards)
+}
+
+// g = -A r over all rows (one warp per row)
+__device__ void true_gradient(const float* __restrict__ Ainst, int d, int m, const double* r, double* g, const DenseSmem& S, Ctx& cx) {
+    for (int v = cx.warp; v < m; v += cx.nwarp) {
+        const double w = row_dot<double>(cx, Ainst + (size_t)S.arow[v] * d, r, d);
+        if (cx.lane == 0) g[v] = -w;
+    }
+    __syncthreads();
+}
+
+__device__ double kkt_residual(const double* lam, const double* g, int m, Ctx& cx) {
+    double res = 0.0;
+    for (int v = cx.tid; v < m; v += cx.nthr) {
+        double t = lam[v] - g[v];
+        t = t < 0.0 ? 0.0 : t;
+        const double w = fabs(lam[v] - t);
+        res = w > res ? w : res;
+    }
+    return cx.block_max(res);
+}
+
+template <class TIO>
+__global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
+    extern __shared__ __align__(16) char dsm[];
+    __shared__ double red[64];
+    __shared__ int s_next, s_nf, s_same, s_cnt;
+    int* ctrl = (int*)(p.ws + p.L.ctrl);
+    const int* list = (const int*)(p.ws + p.L.list);
+    int* flag = (int*)(p.ws + p.L.flag);
+    const int n_slots = (int)p.L.n_slots, mp = (int)p.L.m_pad;
+    int n_round = ctrl[0] - p.round * n_slots;
+    n_round = n_round < n_slots ? n_round : n_slots;
+    if (n_round <= 0) return;
+    Ctx cx(red);
+    const int tid = cx.tid;
+    DenseSmem S;
+    {
+        char* o = dsm;
+        S.lam = (double*)o; o += (size_t)mp * 8; S.lamt = (double*)o; o += (size_t)mp * 8;
+        S.g = (double*)o; o += (size_t)mp * 8; S.gt = (double*)o; o += (size_t)mp * 8;
+        S.dir = (double*)o; o += (size_t)mp * 8; S.bb = (double*)o; o += (size_t)mp * 8;
+        S.fl = (int*)o; o += (size_t)mp * 4; S.flp = (int*)o; o += (size_t)mp * 4;
+        S.arow = (int*)o; o += (size_t)mp * 4; S.sup = (int*)o; o += (size_t)mp * 4;
+        S.xs = (float*)o; o += (size_t)mp * 4;
+        S.As = (float*)o; o += (size_t)kKS * kRC * 4; S.Bs = (float*)o; o += (size_t)kKS * kNB * 4;
+        S.Dt = (float*)o; o += (size_t)kNB * kNB * 4;
+        S.D = (float*)o; o += (size_t)kNB * (kNB + 1) * 4; S.invd = (float*)o;
+    }
+    const TIO* pred_all = (const TIO*)p.pred;
+    TIO* grad_all = (TIO*)p.grad;
+    TIO* proj_all = (TIO*)p.proj;
+    EpiParams ep; ep.mode = p.mode; ep.inner_ratio = p.inner_ratio; ep.sign = p.sign; ep.gscale = p.gscale;
+    constexpr double kEps = 2.220446049250313e-16;
+
+    for (;;) {
+        if (tid == 0) s_next = atomicAdd(&ctrl[1], 1);
+        __syncthreads();
+        const int s = s_next;
+        __syncthreads();
+        if (s >= n_round) break;
+        const int b = list[p.round * n_slots + s];
+        const size_t q = p.inst_index ? (size_t)p.inst_index[b] : (size_t)b;
+        const int m = p.ngen[q], d = p.d;
+        const float* Ainst = p.A + q * (size_t)p.m_max * d;
+        const int4* gen = p.gen + q * (size_t)p.m_max;
+        const float* G = (const float*)(p.ws + p.L.G) + (size_t)s * mp * mp;
+        float* W = (float*)(p.ws + p.L.W) + (size_t)s * mp * mp;
+        const double* bsrc = (const double*)(p.ws + p.L.bvec) + (size_t)s * mp;
+        const float* l1src = (const float*)(p.ws + p.L.l1) + (size_t)s * mp;
+        double* vec = (double*)(p.ws + p.L.vec) + (size_t)s * p.L.vec_doubles;
+        double* r = vec;                                        // [d]  r = c - A^T lam
+        double* rt = vec + p.L.d_pad;                           // [d]  trial residual
+        TIO* c = (TIO*)(vec + 2 * p.L.d_pad);                   // [d]  c = sign * pred
+        const TIO* pred = pred_all + (size_t)b * d;
+
+        // ---- setup
+        double cc = 0.0, l1m = 0.0, dmax = 0.0;
+        for (int k = tid; k < d; k += kDT) { const TIO vc = (TIO)(p.sign * (double)pred[k]); c[k] = vc; r[k] = (double)vc; cc += (double)vc * (double)vc; }
+        for (int v = tid; v < mp; v += kDT) {
+            const bool in = v < m;
+            S.bb[v] = in ? bsrc[v] : 0.0; S.lam[v] = 0.0; S.lamt[v] = 0.0; S.g[v] = in ? -bsrc[v] : 0.0; S.gt[v] = 0.0; S.dir[v] = 0.0;
+            S.arow[v] = in ? gen[v].x : 0;
+            if (in) { const double l = (double)l1src[v]; l1m = l > l1m ? l : l1m; const double gd = (double)G[(size_t)v * mp + v]; dmax = gd > dmax ? gd : dmax; }
+        }
+        cc = cx.block_sum(cc);
+        cx.block_max2(l1m, dmax);
+        const double cnorm = sqrt(cc);
+        const bool finite_in = cc < 1e300;
+        int status = ST_BADINPUT, iters = 0;
+        bool handed_back = false;
+        if (finite_in) {
+            const double scale = (l1m > 1.0 ? l1m : 1.0) * (cnorm > 1e-30 ? cnorm : 1e-30);
+            const double tol = (p.tol > 0 ? p.tol : 1e-12) * scale;
+            const double tolG = 1e-6 * scale > tol ? 1e-6 * scale : tol;
+            const int max_it1 = p.max_iter > 0 ? p.max_iter : 60, max_it2 = 24;
+            const int max_ls = p.max_ls > 0 ? p.max_ls : 40;
+            const float regf = (float)(1e-6 * dmax), floorf_ = (float)(1e-7 * dmax);
+            int nf_fact = -1;                           // size of the free set the factor in W belongs to (-1: none)
+            double f = 0.0;                             // phase 1: q(lam);  phase 2: 1/2 ||r||^2
+            int phase = 1, since_best = 0, it1 = 0, it2 = 0;
+            double res_best = 1e300;
+            double* lam = S.lam; double* lamt = S.lamt; double* g = S.g; double* gt = S.gt;
+            double* rc = r; double* rtr = rt;
+            status = ST_ITER_CAP;
+            for (;;) {
+                double res = kkt_residual(lam, g, m, cx);
+                if (phase == 1 && (res <= tolG || it1 >= max_it1)) {
+                    if (res > 1e-4 * scale) { handed_back = true; break; }       // the Gram-space iteration did not settle
+                    // ---- switch to the true problem: r = c - A^T lam, g = -A r
+                    phase = 2; since_best = 0; res_best = 1e300;
+                    f = 0.5 * true_residual<TIO>(Ainst, d, m, lam, c, rc, S, cx, &s_cnt);
+                    true_gradient(Ainst, d, m, rc, g, S, cx);
+                    res = kkt_residual(lam, g, m, cx);
+                }
+                if (phase == 2) {
+                    if (!(res > tol)) { status = ST_CONVERGED; break; }
+                    if (res < 0.5 * res_best) { res_best = res; since_best = 0; }
+                    else if (++since_best >= 4 && res <= 1e3 * tol) { status = ST_CONVERGED; break; }
+                    if (it2 >= max_it2) {
+                        status = res <= 1e3 * tol ? ST_CONVERGED : ST_ITER_CAP;
+                        if (res > 1e-8 * scale) handed_back = true;
+                        break;
+                    }
+                    ++it2;
+                } else {
+                    ++it1;
+                }
+                ++iters;
+                // ---- free set (ordered); binding variables take a gradient step
+                const double epsb = res < 1e-3 ? res : 1e-3;
+                if (cx.warp == 0) {
+                    int cnt = 0; bool same = true;
+                    for (int v0 = 0; v0 < m; v0 += 32) {
+                        const int v = v0 + cx.lane;
+                        const bool isf = v < m && !(lam[v] <= epsb && g[v] > 0.0);
+                        const unsigned mk = __ballot_sync(0xffffffffu, isf);
+                        if (isf) {
+                            const int pos = cnt + __popc(mk & ((1u << cx.lane) - 1u));
+                            if (pos >= nf_fact || S.flp[pos] != v) same = false;
+                            S.fl[pos] = v;
+                        }
+                        cnt += __popc(mk);
+                    }
+                    same = __all_sync(0xffffffffu, same) && cnt == nf_fact;
+                    if (cx.lane == 0) { s_nf = cnt; s_same = same ? 1 : 0; }
+                }
+                for (int v = tid; v < m; v += kDT) S.dir[v] = g[v];
+                __syncthreads();
+                const int nf = s_nf;
+                const bool same = s_same != 0;
+                if (nf > 0) {
+                    if (!same) {
+                        // gather the free block: W[a][b'] = G[F[a]][F[b']] (b' <= a) + reg on the diagonal, then factor
+                        for (int a = cx.warp; a < nf; a += cx.nwarp) {
+                            const float* grow = G + (size_t)S.fl[a] * mp;
+                            float* wrow = W + (size_t)a * mp;
+                            for (int bq = cx.lane; bq <= a; bq += 32) wrow[bq] = grow[S.fl[bq]] + (bq == a ? regf : 0.0f);
+                        }
+                        for (int a = tid; a < nf; a += kDT) S.flp[a] = S.fl[a];
+                        __syncthreads();
+                        chol_blocked(W, mp, nf, floorf_, S, tid);
+                        nf_fact = nf;
+                    }
+                    for (int a = tid; a < nf; a += kDT) S.xs[a] = (float)g[S.fl[a]];
+                    __syncthreads();
+                    chol_solve_blocked(W, mp, nf, S, tid);
+                    for (int a = tid; a < nf; a += kDT) S.dir[S.fl[a]] = (double)S.xs[a];
+                }
+                __syncthreads();
+                // ---- Armijo along the projection arc
+                double alpha = 1.0, ft = f;
+                bool ok = false, at_floor = false;
+                for (int ls = 0; ls < max_ls; ++ls) {
+                    double dec = 0.0;
+                    for (int v = tid; v < mp; v += kDT) {
+                        double t = 0.0;
+                        if (v < m) { t = lam[v] - alpha * S.dir[v]; if (t < 0.0) t = 0.0; dec += g[v] * (lam[v] - t); }
+                        lamt[v] = t;
+                    }
+                    dec = cx.block_sum(dec);
+                    if (phase == 1) {
+                        double lg, lb;
+                        gram_matvec(G, mp, m, lamt, S.bb, gt, cx, lg, lb);
+                        ft = 0.5 * lg - 0.5 * lb;
+                    } else {
+                        ft = 0.5 * true_residual<TIO>(Ainst, d, m, lamt, c, rtr, S, cx, &s_cnt);
+                    }
+                    const double fa = fabs(f);
+                    if (ls == 0 && fabs(dec) <= 16.0 * kEps * fa && fabs(ft - f) <= 16.0 * kEps * fa) { ok = true; at_floor = true; break; }
+                    if (ft <= f - 1e-4 * dec + 4.0 * kEps * fa) { ok = true; break; }
+                    alpha *= 0.5;
+                }
+                if (!ok) {
+                    // the current point stays; in phase 1 a stall close to the solution still goes on to the true problem
+                    if (phase == 1 && res <= 1e-4 * scale) { it1 = max_it1; continue; }
+                    status = (phase == 2 && res <= 1e3 * tol) ? ST_CONVERGED : ST_STALLED;
+                    if (phase == 1 || res > 1e-8 * scale) handed_back = true;
+                    break;
+                }
+                { double* t1 = lam; lam = lamt; lamt = t1; }
+                f = ft;
+                if (phase == 1) { double* t2 = g; g = gt; gt = t2; }
+                else {
+                    { double* t3 = rc; rc = rtr; rtr = t3; }
+                    true_gradient(Ainst, d, m, rc, g, S, cx);
+                    if (at_floor) { status = ST_CONVERGED; break; }
+                }
+                __syncthreads();
+            }
+            __syncthreads();
+            if (!handed_back && rc != r) {          // the epilogue reads r
+                for (int k = tid; k < d; k += kDT) r[k] = rc[k];
+            }
+            __syncthreads();
+        }
+        if (handed_back) {
+            if (tid == 0) flag[b] = 0;               // the Lawson-Hanson path (general solve kernel, launched next) takes it
+        } else {
+            Instance in;
+            in.A = Ainst; in.gen = (const gen_t*)gen; in.ctype = p.ctype + q * p.dpad; in.avg = p.avg + q * p.dpad;
+            in.d = d; in.ngen = m; in.gen_nnz = 0; in.nvalid = m; in.nsingc = 0; in.csr_ok = 0;
+            in.ghash = nullptr; in.pcol = nullptr; in.pval = nullptr; in.maxl1 = 0.f; in.maxl2 = 0.f;
+            epilogue<double, TIO, const TIO*>(cx, in, ep, c, r, p.mode != MODE_HEURISTIC, false, grad_all + (size_t)b * d,
+                                              proj_all ? proj_all + (size_t)b * d : nullptr, p.loss64 + b, p.rnorm64 + b);
+            if (tid == 0) { p.status[b] = status | ST_PATH_GRAM; p.iters[b] = iters; }
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_dense_solve(const DenseParams& p, cudaStream_t stream) {
+    const size_t smem = dense_solve_smem(p.L.m_pad);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = p.io_f32 ? cudaFuncSetAttribute(dense_solve_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                             : cudaFuncSetAttribute(dense_solve_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)(p.L.n_slots < sms ? p.L.n_slots : sms);
+    if (p.io_f32) dense_solve_kernel<float><<<grid, kDT, smem, stream>>>(p);
+    else dense_solve_kernel<double><<<grid, kDT, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace cave

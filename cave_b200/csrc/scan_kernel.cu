@@ -571,8 +571,10 @@ cudaError_t launch_scan(const ScanParams& p0, cudaStream_t stream) {
         if (smem > 113 * 1024 || (sdepth && sdepth[0] == '3')) { S = 3; smem = scan_rows_smem_bytes(p.d, p.m_max, NT / 32, 3, &rowbuf); }
         if (smem <= 220 * 1024 && !(force && force[0] == 't')) {
             p.stage_stride = rowbuf; p.R = 1; p.stages = S;
-            static size_t configured2 = 0, configured3 = 0;
-            size_t& conf = S == 2 ? configured2 : configured3;
+            static size_t configured2[64] = {0}, configured3[64] = {0};     // per device: the attribute is a per-device property
+            int dev = 0;
+            if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+            size_t& conf = S == 2 ? configured2[dev] : configured3[dev];
             if (smem > conf) {
                 cudaError_t e = S == 2 ? cudaFuncSetAttribute(scan_rows_kernel<NT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                        : cudaFuncSetAttribute(scan_rows_kernel<NT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -592,11 +594,13 @@ cudaError_t launch_scan(const ScanParams& p0, cudaStream_t stream) {
     while (smem > 200 * 1024 && stages > 2) { --stages; smem = scan_smem_bytes(p.d, R, stages, &stride); }
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     p.R = R; p.stages = stages; p.stage_stride = stride;
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (smem > configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(scan_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured[dev] = smem;
     }
     scan_kernel<NT><<<dim3((unsigned)p.B), dim3(NT), smem, stream>>>(p);
     return cudaGetLastError();

@@ -40,6 +40,8 @@ struct SolveParams {
     int cfg_id;
     const unsigned long long* plan;
     const int* order;      // nullable: work-queue position -> instance (most expensive first)
+    const int* dense_flag; // nullable: [B] 1 = the dense (Gram) path owns this batch position, skip it here
+    long long n_packed;    // instances in the pack (inst_index values must be below it)
 };
 
 struct FinalizeParams {

@@ -33,7 +33,15 @@ __global__ void __launch_bounds__(CAVE_LB_T, CAVE_LB_C) solve_kernel(SolveParams
         __syncthreads();
         if (slot_b >= p.B) break;
         const int b = p.order ? p.order[slot_b] : slot_b;
-        const size_t q = p.inst_index ? (size_t)p.inst_index[b] : (size_t)b;     // instance of the pack / of A
+        if (p.dense_flag && p.dense_flag[b]) continue;                            // solved by the dense (Gram) path
+        const long long qi = p.inst_index ? (long long)p.inst_index[b] : (long long)b;
+        if (qi < 0 || qi >= p.n_packed) {
+            // an index outside the pack (stale permutation, another shard's index): report, never read out of bounds
+            if (cx.tid == 0) { p.loss64[b] = NAN; p.rnorm64[b] = NAN; p.status[b] = ST_BADINPUT; p.iters[b] = 0; }
+            for (int k = cx.tid; k < p.d; k += cx.nthr) { grad[(size_t)b * p.d + k] = (TIO)NAN; if (proj) proj[(size_t)b * p.d + k] = (TIO)NAN; }
+            continue;
+        }
+        const size_t q = (size_t)qi;     // instance of the pack / of A
         Instance in;
         in.A = p.A ? p.A + q * p.m_max * p.d : nullptr;
         in.gen = p.gen + q * p.m_max;
@@ -53,11 +61,14 @@ __global__ void __launch_bounds__(CAVE_LB_T, CAVE_LB_C) solve_kernel(SolveParams
 
 template <class T, class TIO>
 cudaError_t launch_solve_t(const SolveParams& p, int grid, int threads, cudaStream_t stream) {
-    static int configured = 0;
-    if (configured < p.smem_bytes) {
+    // the attribute is per device (and cheap to set): no process-wide cache, so a second GPU in the same process works
+    static int configured[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
+    if (dev < 0 || configured[dev] < p.smem_bytes) {
         cudaError_t e = cudaFuncSetAttribute(solve_kernel<T, TIO>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes);
         if (e != cudaSuccess) return e;
-        configured = p.smem_bytes;
+        if (dev >= 0) configured[dev] = p.smem_bytes;
     }
     solve_kernel<T, TIO><<<grid, threads, p.smem_bytes, stream>>>(p);
     return cudaGetLastError();

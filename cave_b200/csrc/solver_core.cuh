@@ -38,7 +38,7 @@ typedef float4 f4_t;
 typedef ulonglong2 hash_t;
 #endif
 
-enum { ST_CONVERGED = 0, ST_ITER_CAP = 1, ST_STALLED = 2, ST_NOSPACE = 3, ST_SKIPPED = 4, ST_BADINPUT = 5, ST_PATH_LH = 0x100 };
+enum { ST_CONVERGED = 0, ST_ITER_CAP = 1, ST_STALLED = 2, ST_NOSPACE = 3, ST_SKIPPED = 4, ST_BADINPUT = 5, ST_PATH_LH = 0x100, ST_PATH_GRAM = 0x200 };
 enum { MODE_EXACT = 0, MODE_INNER = 1, MODE_HEURISTIC = 2 };
 
 struct SolveOpts {

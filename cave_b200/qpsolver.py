@@ -24,11 +24,16 @@ _PRECISIONS = {"fp64": _lib.F64, "float64": _lib.F64, "double": _lib.F64,
                "fp32": _lib.F32, "float32": _lib.F32, "single": _lib.F32}
 
 
+_DENSE = {"auto": 0, None: 0, True: 1, False: -1, "on": 1, "off": -1}
+
+
 def _opts(max_iter=None, max_linesearch=None, tol=None, cap_rows=None, cap_nnz=None, warm=False,
-          index=None, n_packed=0) -> _lib.SolverOpts:
+          index=None, n_packed=0, dense="auto", dense_slots=None) -> _lib.SolverOpts:
+    if dense not in _DENSE:
+        raise ValueError("dense must be 'auto', True or False")
     return _lib.SolverOpts(int(max_iter or 0), int(max_linesearch or 0), float(tol or 0.0),
-                           int(cap_rows or 0), int(cap_nnz or 0), int(bool(warm)), 0,
-                           index.data_ptr() if index is not None else None, int(n_packed))
+                           int(cap_rows or 0), int(cap_nnz or 0), int(bool(warm)), _DENSE[dense],
+                           index.data_ptr() if index is not None else None, int(n_packed), int(dense_slots or 0))
 
 
 def _device_of(t: torch.Tensor, device) -> torch.device:
@@ -109,7 +114,7 @@ def cave_forward_backward(pred_cost: torch.Tensor, tight_ctrs: torch.Tensor, sig
                           want_proj: bool = False, want_status: bool = False, pack: CavePack | None = None,
                           index: torch.Tensor | None = None,
                           m_rows: torch.Tensor | None = None, device=None, max_iter=None, max_linesearch=None,
-                          tol=None, cap_rows=None, cap_nnz=None) -> dict:
+                          tol=None, cap_rows=None, cap_nnz=None, dense="auto", dense_slots=None) -> dict:
     """One call of the hot path through the C ABI.  Returns a dict with ``loss`` (scalar for
     mean/sum, [B] for none), ``loss_i`` [B], ``grad`` [B, d] (= d loss / d pred_cost for an upstream
     gradient of one), and optionally ``proj``, ``rnorm``, ``status``, ``iters`` — all on the
@@ -118,7 +123,7 @@ def cave_forward_backward(pred_cost: torch.Tensor, tight_ctrs: torch.Tensor, sig
     if index is not None:
         return _forward_backward_indexed(lib, pred_cost, tight_ctrs, sign, mode, inner_ratio, reduction, precision,
                                          want_proj, want_status, pack, index, device, max_iter, max_linesearch, tol,
-                                         cap_rows, cap_nnz)
+                                         cap_rows, cap_nnz, dense, dense_slots)
     if pred_cost.dim() != 2 or tight_ctrs.dim() != 3 or tight_ctrs.shape[0] != pred_cost.shape[0] \
             or tight_ctrs.shape[2] != pred_cost.shape[1]:
         raise ValueError(f"shape mismatch: pred_cost {tuple(pred_cost.shape)}, tight_ctrs {tuple(tight_ctrs.shape)}")
@@ -139,7 +144,7 @@ def cave_forward_backward(pred_cost: torch.Tensor, tight_ctrs: torch.Tensor, sig
         A = torch.zeros((B, 1, d), dtype=torch.float32, device=dev)
         m = 1
     compute = _PRECISIONS[precision]
-    opts = _opts(max_iter, max_linesearch, tol, cap_rows, cap_nnz, warm=pack is not None)
+    opts = _opts(max_iter, max_linesearch, tol, cap_rows, cap_nnz, warm=pack is not None, dense=dense, dense_slots=dense_slots)
     nb = ctypes.c_size_t()
     if pack is not None:
         if pack.shape != (B, m, d) or pack.buf.device != dev:
@@ -175,7 +180,8 @@ def cave_forward_backward(pred_cost: torch.Tensor, tight_ctrs: torch.Tensor, sig
 
 
 def _forward_backward_indexed(lib, pred_cost, ctrs, sign, mode, inner_ratio, reduction, precision, want_proj,
-                              want_status, pack, index, device, max_iter, max_linesearch, tol, cap_rows, cap_nnz) -> dict:
+                              want_status, pack, index, device, max_iter, max_linesearch, tol, cap_rows, cap_nnz,
+                              dense="auto", dense_slots=None) -> dict:
     """Batch = rows ``index`` of a dataset whose constraints were packed once (device-resident dataset)."""
     if pack is None:
         raise ValueError("index= needs pack= (pack_constraints over the whole dataset)")
@@ -195,7 +201,8 @@ def _forward_backward_indexed(lib, pred_cost, ctrs, sign, mode, inner_ratio, red
         raise ValueError("the dense dataset tensor must be the float32 CUDA tensor the pack was built from")
     B = pred.shape[0]
     compute = _PRECISIONS[precision]
-    opts = _opts(max_iter, max_linesearch, tol, cap_rows, cap_nnz, warm=True, index=idx, n_packed=N)
+    opts = _opts(max_iter, max_linesearch, tol, cap_rows, cap_nnz, warm=True, index=idx, n_packed=N, dense=dense,
+                 dense_slots=dense_slots)
     nb = ctypes.c_size_t()
     _lib.check(lib.cave_scratch_bytes(B, m, d, compute, ctypes.byref(opts), ctypes.byref(nb)))
     scratch = torch.empty(nb.value, dtype=torch.uint8, device=dev)
@@ -219,6 +226,30 @@ def _forward_backward_indexed(lib, pred_cost, ctrs, sign, mode, inner_ratio, red
     if want_status:
         out["status"], out["iters"], out["rnorm"] = status, iters, rnorm
     return out
+
+
+def dense_gram(tight_ctrs: torch.Tensor, dense_slots=None) -> tuple[torch.Tensor, int]:
+    """Diagnostic: G~ = A A^T of every (dense) instance from the tensor-core Gram kernel alone (``cave_dense_gram``):
+    returns ``(G [B, m_pad, m_pad] float32, number of instances the device classified as dense)``."""
+    lib = _lib.load()
+    A = tight_ctrs.detach()
+    if not A.is_cuda or A.dtype != torch.float32 or not A.is_contiguous() or A.dim() != 3:
+        raise ValueError("tight_ctrs must be a contiguous float32 CUDA tensor [B, m, d]")
+    B, m, d = A.shape
+    opts = _opts(dense=True, dense_slots=dense_slots or B)
+    nb = ctypes.c_size_t()
+    _lib.check(lib.cave_pack_bytes(B, m, d, ctypes.byref(nb)))
+    pack_buf = torch.empty(nb.value, dtype=torch.uint8, device=A.device)
+    _lib.check(lib.cave_scratch_bytes(B, m, d, _lib.F64, ctypes.byref(opts), ctypes.byref(nb)))
+    scratch = torch.empty(nb.value, dtype=torch.uint8, device=A.device)
+    m_pad = (m + 127) // 128 * 128
+    G = torch.zeros((B, m_pad, m_pad), dtype=torch.float32, device=A.device)
+    cnt = torch.zeros(1, dtype=torch.int32, device=A.device)
+    with torch.cuda.device(A.device):
+        stream = torch.cuda.current_stream(A.device).cuda_stream
+        _lib.check(lib.cave_dense_gram(_ptr(A), B, m, d, ctypes.byref(opts), _ptr(G), _ptr(cnt), _ptr(pack_buf), pack_buf.numel(),
+                                       _ptr(scratch), scratch.numel(), ctypes.c_void_p(stream)))
+    return G, int(cnt.item())
 
 
 def project_cuda(tight_ctrs: torch.Tensor, signed_cost: torch.Tensor, precision: str = "fp64",

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CAVE_B200_ABI_VERSION 3
+#define CAVE_B200_ABI_VERSION 4
 
 /* error codes */
 #define CAVE_OK 0
@@ -64,6 +64,7 @@ extern "C" {
 #define CAVE_ST_SKIPPED 4       /* heuristic mode or empty cone: no solve was needed       */
 #define CAVE_ST_BADINPUT 5      /* NaN / Inf in the prediction: no solve, outputs are NaN  */
 #define CAVE_ST_PATH_LH 0x100   /* flag: solved by the Lawson-Hanson path (else Newton)    */
+#define CAVE_ST_PATH_GRAM 0x200 /* flag: solved by the dense path (tensor-core Gram + Gram-space Newton) */
 
 typedef struct cave_solver_opts {
     int32_t max_iter;        /* Newton iterations / LH pivots cap; <= 0 -> default (200 / 3*m) */
@@ -74,7 +75,10 @@ typedef struct cave_solver_opts {
                                 <= 0 -> m_max                                                  */
     int64_t cap_nnz;         /* scratch sizing: max non-zeros in those rows; <= 0 -> cap_rows*d */
     int32_t warm_pack;       /* 1: `pack` already holds cave_pack() output for this A          */
-    int32_t reserved;
+    int32_t dense_mode;      /* dense (tensor-core Gram) path for instances without singleton rows and >= 128 rows:
+                                0 auto (enabled when 128 <= m_max <= d: structured models always have m > d),
+                                1 on (any instance with 128 <= rows <= 2048 and no singleton row), -1 off.
+                                When on, cave_scratch_bytes() includes the Gram workspace.                */
     /* Device-resident dataset (optional, needs warm_pack): `pack` was built by cave_pack() over ALL
      * n_packed instances of a dataset ([n_packed, m_max, d]); instance b of this call is dataset instance
      * inst_index[b] (device pointer, int32[B], values in [0, n_packed)).  `A` is then the dataset tensor,
@@ -82,6 +86,8 @@ typedef struct cave_solver_opts {
      * CAVE_ST_NOSPACE).  Replaces DataLoader + collate_fn re-padding every batch (src/dataset.py:133-144). */
     const int32_t* inst_index;
     int64_t n_packed;        /* 0 / ignored unless inst_index is set                                   */
+    int64_t dense_slots;     /* dense path: instances whose Gram workspace is resident at once (the batch is processed
+                                in ceil(B / dense_slots) rounds); <= 0 -> default (4 per SM, at most ~12 GiB)      */
 } cave_solver_opts;
 
 typedef struct cave_limits {
@@ -138,6 +144,17 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
                           int32_t* status, int32_t* iters,
                           void* pack, size_t pack_bytes, void* scratch, size_t scratch_bytes,
                           void* stream);
+
+/* Diagnostic for the dense regime (north_star item 1): runs cave_pack() on A and then only the TF32 split and the
+ * tensor-core Gram kernel (TMA tiles -> tcgen05.mma, 3xTF32, float32 accumulation in TMEM) for the first
+ * min(B, slots) instances, and copies G~ = A A^T of instance i to G_out[i] as a row-major [m_pad, m_pad] float32
+ * matrix (m_pad = m_max rounded up to 128; rows are the VALID rows of A in order; entries beyond the valid rows of
+ * an instance's last 128-row block are zero, beyond that block unspecified).  Every instance must be dense
+ * (no singleton row, >= 128 valid rows).  The parity tests compare it with a float64 product of the same rows.
+ * scratch must hold cave_scratch_bytes() with dense_mode = 1. */
+int cave_dense_gram(const float* A, int64_t B, int64_t m_max, int64_t d, const cave_solver_opts* opts,
+                    float* G_out, int32_t* n_dense_out, void* pack, size_t pack_bytes,
+                    void* scratch, size_t scratch_bytes, void* stream);
 
 #ifdef __cplusplus
 }

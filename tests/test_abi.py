@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_version_limits_and_sizes(lib):
     from cave_b200 import _lib
-    assert lib.cave_abi_version() == 3
+    assert lib.cave_abi_version() == 4
     lim = _lib.Limits()
     assert lib.cave_get_limits(ctypes.byref(lim)) == 0
     assert lim.max_d >= 4950 and lim.max_m >= 5200
@@ -46,6 +46,15 @@ def test_version_limits_and_sizes(lib):
     small = n.value
     assert lib.cave_scratch_bytes(4096, 1337, 1225, _lib.F64, None, ctypes.byref(n)) == 0
     assert n.value > small
+    # dense (tensor-core Gram) path: its workspace is part of the scratch only where the host gate enables it
+    assert lib.cave_scratch_bytes(512, 1024, 1225, _lib.F64, None, ctypes.byref(n)) == 0          # auto: m_max <= d
+    with_dense = n.value
+    off = _lib.SolverOpts(0, 0, 0.0, 0, 0, 0, -1)
+    assert lib.cave_scratch_bytes(512, 1024, 1225, _lib.F64, ctypes.byref(off), ctypes.byref(n)) == 0
+    assert with_dense > n.value + 512 * 1024 * 1024 * 4
+    on = _lib.SolverOpts(0, 0, 0.0, 128, 20000, 0, 1)
+    assert lib.cave_scratch_bytes(4096, 1337, 1225, _lib.F64, ctypes.byref(on), ctypes.byref(n)) == 0
+    assert n.value > small + (1 << 30)
 
 
 def test_argument_errors_are_codes_with_messages(lib):

@@ -23,8 +23,9 @@ from ._pyepo_compat import EPO, optModule
 from .qpsolver import CavePack, cave_forward_backward, project_cuda
 
 _REFERENCE_SOLVERS = ("apgd", "clarabel", "nnls")
-_KERNEL_KWARGS = ("precision", "max_iter", "max_linesearch", "tol", "cap_rows", "cap_nnz", "device", "pack", "m_rows", "index",
-                  "dense", "dense_slots")
+# constructor-level solver_kwargs: properties of the solver, never of one particular batch (a pack, an index or a row-count
+# hint belongs to a call; accepted here they would silently apply to every later batch)
+_KERNEL_KWARGS = ("precision", "max_iter", "max_linesearch", "tol", "cap_rows", "cap_nnz", "device", "dense", "dense_slots", "strict")
 
 
 class _CaveCudaFunction(torch.autograd.Function):
@@ -36,7 +37,16 @@ class _CaveCudaFunction(torch.autograd.Function):
         if isinstance(tight_ctrs, CavePack):      # device-resident dataset: kwargs carries index=
             kwargs = dict(kwargs, pack=tight_ctrs)
             tight_ctrs = None
-        out = cave_forward_backward(pred_cost, tight_ctrs, sign, mode, inner_ratio, reduction, **kwargs)
+        strict = bool(kwargs.get("strict", False))
+        kwargs = {k: v for k, v in kwargs.items() if k != "strict"}
+        out = cave_forward_backward(pred_cost, tight_ctrs, sign, mode, inner_ratio, reduction, want_status=strict, **kwargs)
+        if strict:      # opt-in (synchronises): scipy's nnls raises at its iteration limit, so does this
+            st = out["status"] & 0xff
+            bad = (st != _lib.ST_CONVERGED) & (st != _lib.ST_SKIPPED)
+            if bool(bad.any()):
+                codes, counts = torch.unique(st[bad], return_counts=True)
+                raise RuntimeError("solver='cuda': %d of %d instances did not converge (status: count) %s"
+                                   % (int(bad.sum()), st.numel(), dict(zip(codes.tolist(), counts.tolist()))))
         grad, loss = out["grad"], out["loss"]
         if grad.device != pred_cost.device:       # host tensors in -> host tensors out
             if pred_cost.device.type == "cpu" and pred_cost.is_pinned():
@@ -80,15 +90,21 @@ class abstractConeAlignedCosine(optModule):
     def _mode(self) -> int:
         raise NotImplementedError
 
-    def forward(self, pred_cost: torch.Tensor, tight_ctrs, index: torch.Tensor | None = None) -> torch.Tensor:
+    def forward(self, pred_cost: torch.Tensor, tight_ctrs, index: torch.Tensor | None = None,
+                pack: CavePack | None = None, m_rows: torch.Tensor | None = None) -> torch.Tensor:
         """``tight_ctrs``: the reference's padded [B, m, d] tensor (src/cave.py:55-57) — or, as an extension,
         a ``CavePack`` built once over the whole dataset together with ``index`` [B] (dataset instance of
-        every batch row), which keeps the constraints resident on the device across epochs."""
+        every batch row), which keeps the constraints resident on the device across epochs.  ``pack`` (a warm
+        pack of exactly this ``tight_ctrs`` tensor) and ``m_rows`` are per-call arguments."""
         sign = self._sign()
         mode = self._mode()
         kw = self._kernel_kwargs()
         if index is not None:
             kw = dict(kw, index=index)
+        if pack is not None:
+            kw = dict(kw, pack=pack)
+        if m_rows is not None:
+            kw = dict(kw, m_rows=m_rows)
         return _CaveCudaFunction.apply(pred_cost, tight_ctrs, sign, mode, getattr(self, "inner_ratio", 0.0),
                                        self.reduction, kw)
 
@@ -114,7 +130,7 @@ class exactConeAlignedCosine(abstractConeAlignedCosine):
         return _lib.MODE_EXACT
 
     def _get_projection(self, signed_cost: torch.Tensor, tight_ctrs: torch.Tensor) -> torch.Tensor:
-        kw = {k: v for k, v in self._kernel_kwargs().items() if k != "pack"}
+        kw = {k: v for k, v in self._kernel_kwargs().items() if k != "strict"}
         proj, _ = project_cuda(tight_ctrs, signed_cost, **kw)
         return proj / proj.norm(dim=1, keepdim=True).clamp(min=1e-8)       # src/cave.py:129
 
@@ -150,7 +166,7 @@ class innerConeAlignedCosine(exactConeAlignedCosine):
         return _lib.MODE_INNER
 
     def _get_projection(self, signed_cost: torch.Tensor, tight_ctrs: torch.Tensor) -> torch.Tensor:
-        kw = {k: v for k, v in self._kernel_kwargs().items() if k != "pack"}
+        kw = {k: v for k, v in self._kernel_kwargs().items() if k != "strict"}
         mode = self._mode()
         # the target is what the fused kernel aligns against; recover it through the two-step contract
         avg = _average_ctrs(tight_ctrs)

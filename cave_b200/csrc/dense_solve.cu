@@ -585,6 +585,9 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
         }
         if (handed_back) {
             if (tid == 0) flag[b] = 0;               // the Lawson-Hanson path (general solve kernel, launched next) takes it
+        } else if (!finite_in) {                     // NaN / Inf prediction: reported, never a silent number
+            for (int k = tid; k < d; k += kDT) { grad_all[(size_t)b * d + k] = (TIO)NAN; if (proj_all) proj_all[(size_t)b * d + k] = (TIO)NAN; }
+            if (tid == 0) { p.loss64[b] = NAN; p.rnorm64[b] = NAN; p.status[b] = ST_BADINPUT | ST_PATH_GRAM; p.iters[b] = 0; }
         } else {
             Instance in;
             in.A = Ainst; in.gen = (const gen_t*)gen; in.ctype = p.ctype + q * p.dpad; in.avg = p.avg + q * p.dpad;

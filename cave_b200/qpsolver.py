@@ -74,6 +74,7 @@ class CavePack:
     shape: tuple
     data_ptr: int
     ctrs: torch.Tensor | None = None
+    version: int = 0            # tensor._version of tight_ctrs when it was packed (in-place edits invalidate the pack)
 
     def launch_plan(self, precision: str = "fp64", io_dtype: torch.dtype = torch.float32) -> dict:
         """Diagnostics (synchronises): the solve-kernel configuration the pack's statistics select on the device."""
@@ -106,7 +107,7 @@ def pack_constraints(tight_ctrs: torch.Tensor, m_rows: torch.Tensor | None = Non
     with torch.cuda.device(A.device):
         stream = torch.cuda.current_stream(A.device).cuda_stream
         _lib.check(lib.cave_pack(_ptr(A), _ptr(m_rows), B, m, d, _ptr(buf), nbytes.value, ctypes.c_void_p(stream)))
-    return CavePack(buf, (B, m, d), A.data_ptr(), A if keep_dense else None)
+    return CavePack(buf, (B, m, d), A.data_ptr(), A if keep_dense else None, int(tight_ctrs._version))
 
 
 def cave_forward_backward(pred_cost: torch.Tensor, tight_ctrs: torch.Tensor, sign: float, mode: int,
@@ -147,8 +148,13 @@ def cave_forward_backward(pred_cost: torch.Tensor, tight_ctrs: torch.Tensor, sig
     opts = _opts(max_iter, max_linesearch, tol, cap_rows, cap_nnz, warm=pack is not None, dense=dense, dense_slots=dense_slots)
     nb = ctypes.c_size_t()
     if pack is not None:
-        if pack.shape != (B, m, d) or pack.buf.device != dev:
-            raise ValueError("pack does not belong to this tight_ctrs tensor")
+        # a pack describes ONE tensor: same storage, not modified since (a same-shape batch of other instances would be
+        # projected onto the wrong cones without any error otherwise)
+        if pack.shape != (B, m, d) or pack.buf.device != dev or pack.data_ptr != A.data_ptr() \
+                or pack.version != int(tight_ctrs._version):
+            raise ValueError("pack does not belong to this tight_ctrs tensor (other storage, shape or device, or the "
+                             "tensor was modified in place after pack_constraints); for batches drawn from a dataset "
+                             "pack the whole dataset once and pass index=")
         pack_buf = pack.buf
     else:
         _lib.check(lib.cave_pack_bytes(B, m, d, ctypes.byref(nb)))

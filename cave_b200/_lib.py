@@ -6,7 +6,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_C", "libcave_b200.so")
+# CAVE_B200_LIB: an alternative build of the same library (e.g. the -DCAVE_DENSE_PROFILE build of tools/dense_profile.py)
+LIB_PATH = os.environ.get("CAVE_B200_LIB") or os.path.join(HERE, "_C", "libcave_b200.so")
 
 CAVE_OK = 0
 MODE_EXACT, MODE_INNER, MODE_HEURISTIC = 0, 1, 2
@@ -16,7 +17,7 @@ ST_CONVERGED, ST_ITER_CAP, ST_STALLED, ST_NOSPACE, ST_SKIPPED, ST_BADINPUT, ST_P
 
 EXPORTS = ("cave_abi_version", "cave_last_error", "cave_get_limits", "cave_pack_bytes",
            "cave_scratch_bytes", "cave_pack", "cave_forward_backward", "cave_plan_offset", "cave_plan_choice",
-           "cave_dense_gram")
+           "cave_dense_gram", "cave_launch_count", "cave_dense_ctrl_offset")
 
 
 class SolverOpts(ctypes.Structure):
@@ -50,6 +51,7 @@ def load() -> ctypes.CDLL:
     lib = ctypes.CDLL(LIB_PATH)
     P, I64, I32, F, SZP = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.POINTER(ctypes.c_size_t)
     lib.cave_abi_version.restype = I32
+    lib.cave_launch_count.restype = ctypes.c_uint64
     lib.cave_last_error.restype = ctypes.c_char_p
     lib.cave_get_limits.argtypes = [ctypes.POINTER(Limits)]
     lib.cave_pack_bytes.argtypes = [I64, I64, I64, SZP]
@@ -59,11 +61,12 @@ def load() -> ctypes.CDLL:
                                           ctypes.POINTER(SolverOpts), P, P, P, P, P, P, P,
                                           P, ctypes.c_size_t, P, ctypes.c_size_t, P]
     lib.cave_dense_gram.argtypes = [P, I64, I64, I64, ctypes.POINTER(SolverOpts), P, P, P, ctypes.c_size_t, P, ctypes.c_size_t, P]
+    lib.cave_dense_ctrl_offset.argtypes = [I64, I64, I64, ctypes.POINTER(SolverOpts), SZP]
     lib.cave_plan_offset.argtypes = [I64, I64, I64, SZP]
     IP = ctypes.POINTER(ctypes.c_int)
     lib.cave_plan_choice.argtypes = [ctypes.POINTER(ctypes.c_uint64), I64, I32, I32, IP, IP, IP]
     for name in ("cave_get_limits", "cave_pack_bytes", "cave_scratch_bytes", "cave_pack", "cave_forward_backward",
-                 "cave_plan_offset", "cave_plan_choice", "cave_dense_gram"):
+                 "cave_plan_offset", "cave_plan_choice", "cave_dense_gram", "cave_dense_ctrl_offset"):
         getattr(lib, name).restype = I32
     _lib = lib
     return lib

@@ -33,14 +33,15 @@ def is_fresh() -> bool:
     return all(os.path.getmtime(p) <= t for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and is_fresh():
+def build(force: bool = False, verbose: bool = False, alt_name: str | None = None) -> str:
+    """alt_name: write an alternative build (with CAVE_NVCC_EXTRA flags) next to the product library instead of replacing it."""
+    if alt_name is None and not force and is_fresh():
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
     objs, logs = [], []
     procs = []
     for s in SOURCES:
-        obj = os.path.join(OUT_DIR, s.replace(".cu", ".o"))
+        obj = os.path.join(OUT_DIR, s.replace(".cu", ".o") if alt_name is None else s.replace(".cu", ".alt.o"))
         cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("CAVE_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, s), "-o", obj]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
@@ -49,15 +50,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
         logs.append(f"== {s}\n{out}")
         if pr.returncode != 0:
             raise RuntimeError(f"nvcc failed on {s}:\n{out}")
-    with open(os.path.join(OUT_DIR, "ptxas.log"), "w") as f:
-        f.write("\n".join(logs))
+    if alt_name is None:
+        with open(os.path.join(OUT_DIR, "ptxas.log"), "w") as f:
+            f.write("\n".join(logs))
     if verbose:
         print("\n".join(logs))
-    subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs,
+    target = LIB if alt_name is None else os.path.join(OUT_DIR, alt_name)
+    subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", target, *objs,
                            "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
     import sys
-    print(build(force=True, verbose="-v" in sys.argv))
+    alt = [a for a in sys.argv[1:] if a.endswith(".so")]
+    print(build(force=True, verbose="-v" in sys.argv, alt_name=alt[0] if alt else None))

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/cave_b200.h"
@@ -16,6 +17,7 @@
 namespace {
 
 thread_local std::string g_err;
+std::atomic<unsigned long long> g_launches{0};      // kernels launched by this library in this process (cave_launch_count)
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -107,6 +109,8 @@ extern "C" {
 
 int cave_abi_version(void) { return CAVE_B200_ABI_VERSION; }
 
+unsigned long long cave_launch_count(void) { return g_launches.load(); }
+
 const char* cave_last_error(void) { return g_err.c_str(); }
 
 int cave_get_limits(cave_limits* out) {
@@ -126,6 +130,16 @@ int cave_plan_offset(int64_t B, int64_t m_max, int64_t d, size_t* out) {
     if (!out) return fail(CAVE_EINVAL, "out is null");
     if (int e = check_shape(B, m_max, d)) return e;
     *out = cave::make_pack_layout(B, m_max, d).plan;
+    return CAVE_OK;
+}
+
+int cave_dense_ctrl_offset(int64_t B, int64_t m_max, int64_t d, const cave_solver_opts* opts, size_t* out) {
+    if (!out) return fail(CAVE_EINVAL, "out is null");
+    if (int e = check_shape(B, m_max, d)) return e;
+    int64_t cr, cz;
+    resolve_caps(opts, m_max, d, &cr, &cz);
+    const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, cr, cz, 8, solver_slots(B, cave::solver_slot_bytes(d, cr, cz, 8)));
+    *out = cave::make_dense_layout(B, m_max, d, dense_slots(opts, B, m_max, d), SL.total).ctrl;
     return CAVE_OK;
 }
 
@@ -176,6 +190,7 @@ int cave_pack(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, i
     cudaError_t e = cudaMemsetAsync(base + L.plan, 0, 64, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(CAVE_ECUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
     e = cave::launch_scan(p, (cudaStream_t)stream);
+    g_launches += 1;
     if (e != cudaSuccess) return fail(CAVE_ECUDA, "scan kernel launch failed: %s", cudaGetErrorString(e));
     cave::PlanParams pp;
     memset(&pp, 0, sizeof(pp));
@@ -184,6 +199,7 @@ int cave_pack(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, i
     pp.gen4 = p.gen4; pp.ghash = p.ghash; pp.plan = (unsigned long long*)(base + L.plan);
     pp.okey = (int*)(base + L.okey); pp.order = (int*)(base + L.order);
     e = cave::launch_plan(pp, (cudaStream_t)stream);
+    g_launches += 2;
     if (e != cudaSuccess) return fail(CAVE_ECUDA, "plan kernel launch failed: %s", cudaGetErrorString(e));
     return CAVE_OK;
 }
@@ -261,13 +277,14 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
         cave::DenseParams dp;
         memset(&dp, 0, sizeof(dp));
         dp.A = A; dp.pred = pred; dp.B = (int)B; dp.m_max = (int)m_max; dp.d = (int)d;
-        dp.inst_index = sp.inst_index; dp.nvalid = sp.nvalid; dp.ngen = sp.ngen; dp.nsingc = sp.nsingc; dp.gen = sp.gen;
+        dp.inst_index = sp.inst_index; dp.n_packed = Bpack; dp.nvalid = sp.nvalid; dp.ngen = sp.ngen; dp.nsingc = sp.nsingc; dp.gen = sp.gen;
         dp.ctype = sp.ctype; dp.avg = sp.avg; dp.dpad = PL.dpad;
         dp.ws = sb; dp.L = DL; dp.force = (opts && opts->dense_mode > 0) ? 1 : 0;
         dp.grad = grad; dp.proj = proj; dp.loss64 = sp.loss64; dp.rnorm64 = sp.rnorm64; dp.status = sp.status; dp.iters = sp.iters;
         dp.mode = mode; dp.inner_ratio = inner_ratio; dp.sign = sign; dp.gscale = sp.gscale;
         dp.max_iter = 0; dp.max_ls = sp.max_ls; dp.tol = sp.tol; dp.io_f32 = io_dtype == CAVE_F32; dp.nk = (int)(DL.d_pad / 32);
         ce = cave::launch_dense_list(dp, st);
+        g_launches += 1;
         if (ce != cudaSuccess) return fail(CAVE_ECUDA, "dense list kernel launch failed: %s", cudaGetErrorString(ce));
         const int64_t rounds = (B + DL.n_slots - 1) / DL.n_slots;
         for (int64_t r = 0; r < rounds; ++r) {
@@ -277,6 +294,7 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
             ce = cave::launch_dense_gram(dp, st);
             if (ce != cudaSuccess) return fail(CAVE_ECUDA, "dense Gram kernel launch failed: %s (%s)", cudaGetErrorString(ce), cave::dense_last_error());
             ce = cave::launch_dense_solve(dp, st);
+            g_launches += 3;
             if (ce != cudaSuccess) return fail(CAVE_ECUDA, "dense solve kernel launch failed: %s", cudaGetErrorString(ce));
         }
         sp.dense_flag = (const int*)(sb + DL.flag);
@@ -287,6 +305,7 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
         if (threads < 32 || threads > 256 || threads % 32) threads = 256;
         sp.cfg_id = -1;
         ce = cave::launch_solve(sp, compute_dtype == CAVE_F32, io_dtype == CAVE_F32, (int)n_slots, threads, st);
+        g_launches += 1;
         if (ce != cudaSuccess) return fail(CAVE_ECUDA, "solve kernel launch failed: %s", cudaGetErrorString(ce));
     } else {
         // every candidate configuration is enqueued; the pack's plan statistics select exactly one on the device
@@ -300,6 +319,7 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
             sp.smem_bytes = cfg.smem_bytes;
             sp.cfg_id = (only >= 0 && only < cave::kNumSolveConfigs) ? -1 : i;
             ce = cave::launch_solve(sp, compute_dtype == CAVE_F32, io_dtype == CAVE_F32, (int)grid, cfg.threads, st);
+            g_launches += 1;
             if (ce != cudaSuccess) return fail(CAVE_ECUDA, "solve kernel launch failed: %s", cudaGetErrorString(ce));
         }
     }
@@ -309,6 +329,7 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     fp.B = (int)B; fp.reduction = reduction; fp.loss64 = sp.loss64; fp.rnorm64 = sp.rnorm64; fp.status = sp.status; fp.iters = sp.iters;
     fp.loss = loss; fp.loss_i = loss_i; fp.rnorm = rnorm; fp.status_out = status; fp.iters_out = iters;
     ce = cave::launch_finalize(fp, io_dtype == CAVE_F32, st);
+    g_launches += 1;
     if (ce != cudaSuccess) return fail(CAVE_ECUDA, "finalize kernel launch failed: %s", cudaGetErrorString(ce));
     return CAVE_OK;
 }
@@ -337,7 +358,7 @@ int cave_dense_gram(const float* A, int64_t B, int64_t m_max, int64_t d, const c
     cave::DenseParams dp;
     memset(&dp, 0, sizeof(dp));
     static const float kZero = 0.f;
-    dp.A = A; dp.pred = &kZero; dp.B = (int)B; dp.m_max = (int)m_max; dp.d = (int)d;
+    dp.A = A; dp.pred = &kZero; dp.B = (int)B; dp.m_max = (int)m_max; dp.d = (int)d; dp.n_packed = B;
     dp.nvalid = (const int*)(pb + PL.nvalid); dp.ngen = (const int*)(pb + PL.ngen); dp.nsingc = (const int*)(pb + PL.nsingc);
     dp.gen = (const int4*)(pb + PL.gen); dp.ctype = (const unsigned char*)(pb + PL.ctype); dp.avg = (const float*)(pb + PL.avg);
     dp.dpad = PL.dpad; dp.ws = sb; dp.L = DL; dp.force = 1; dp.sign = 0.0; dp.io_f32 = 1; dp.nk = (int)(DL.d_pad / 32);

@@ -49,7 +49,7 @@ CAVE_HD DenseLayout make_dense_layout(int64_t B, int64_t m_max, int64_t d, int64
     const size_t mp = (size_t)L.m_pad, dp = (size_t)L.d_pad, ns = (size_t)n_slots;
     L.vec_doubles = 8 * mp + 3 * dp + 64;
     size_t o = align_up(base, 1024);
-    L.ctrl = o;   o = align_up(o + 64, 256);
+    L.ctrl = o;   o = align_up(o + 512, 256);     // 16 ints, then 16 x uint64 phase clocks (CAVE_DENSE_PROFILE builds)
     L.list = o;   o = align_up(o + (size_t)B * 4, 256);
     L.flag = o;   o = align_up(o + (size_t)B * 4, 256);
     L.planes = o = align_up(o, 1024); o += ns * 2 * mp * dp * 4;
@@ -75,6 +75,7 @@ struct DenseParams {
     const void* pred;           // [B, d] io dtype
     int B, m_max, d;
     const int* inst_index;      // nullable
+    long long n_packed;         // instances in the pack (bound of inst_index values)
     const int *nvalid, *ngen, *nsingc;
     const int4* gen;            // [*, m_max]
     const unsigned char* ctype; // [*, dpad]

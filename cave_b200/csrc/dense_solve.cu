@@ -122,75 +122,105 @@ __device__ void factor_diag(float* D, float* invd, int nb, float floor_, int tid
     __syncthreads();
 }
 
+// One chunk of the block-column update of the left-looking Cholesky: rows [r0, r0 + 64 RM) x columns [j0, j0 + 64) of W get
+// -= L[rows, 0:j0] L[j0:j0+64, 0:j0]^T.  512 threads, each a micro-tile of RM rows x 8 columns; the k-slabs of both operands
+// go through shared memory k-major (one row per staging thread, next slab prefetched into registers).  RM = 8 interleaves two
+// groups of four rows per thread so that the 128-bit operand loads of a quarter-warp fall into distinct banks.
+template <int RM>
+__device__ __forceinline__ void chol_update_chunk(float* __restrict__ W, int ldw, int nf, int j0, int r0, const DenseSmem& S, int tid) {
+    constexpr int ROWS = 64 * RM;
+    const int tr = tid & 63, tcg = tid >> 6;
+    float acc[RM][8];
+#pragma unroll
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    const bool stage_a = tid < ROWS, stage_b = tid < 64;
+    const int myrow = r0 + tid < nf ? r0 + tid : nf - 1;                // staging: one row per thread (clamped)
+    const int mybrow = j0 + (tid & 63) < nf ? j0 + (tid & 63) : nf - 1;
+    const float* arow = W + (size_t)myrow * ldw;
+    const float* brow = W + (size_t)mybrow * ldw;
+    float4 pa[4], pb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        pa[u] = stage_a ? *reinterpret_cast<const float4*>(arow + u * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        pb[u] = stage_b ? *reinterpret_cast<const float4*>(brow + u * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int p0 = 0; p0 < j0; p0 += kKS) {
+        __syncthreads();                    // previous slab consumed
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (stage_a) {
+                S.As[(u * 4 + 0) * kRC + tid] = pa[u].x; S.As[(u * 4 + 1) * kRC + tid] = pa[u].y;
+                S.As[(u * 4 + 2) * kRC + tid] = pa[u].z; S.As[(u * 4 + 3) * kRC + tid] = pa[u].w;
+            }
+            if (stage_b) {
+                S.Bs[(u * 4 + 0) * kNB + tid] = pb[u].x; S.Bs[(u * 4 + 1) * kNB + tid] = pb[u].y;
+                S.Bs[(u * 4 + 2) * kNB + tid] = pb[u].z; S.Bs[(u * 4 + 3) * kNB + tid] = pb[u].w;
+            }
+        }
+        __syncthreads();
+        if (p0 + kKS < j0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (stage_a) pa[u] = *reinterpret_cast<const float4*>(arow + p0 + kKS + u * 4);
+                if (stage_b) pb[u] = *reinterpret_cast<const float4*>(brow + p0 + kKS + u * 4);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kKS; ++k) {
+            float av[RM];
+            if (RM == 8) {
+                const float4 a0 = *reinterpret_cast<const float4*>(S.As + k * kRC + tr * 4);
+                const float4 a1 = *reinterpret_cast<const float4*>(S.As + k * kRC + 256 + tr * 4);
+                av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
+                av[4 % RM] = a1.x; av[5 % RM] = a1.y; av[6 % RM] = a1.z; av[7 % RM] = a1.w;
+            } else if (RM == 4) {
+                const float4 a0 = *reinterpret_cast<const float4*>(S.As + k * kRC + tr * 4);
+                av[0] = a0.x; av[1 % RM] = a0.y; av[2 % RM] = a0.z; av[3 % RM] = a0.w;
+            } else if (RM == 2) {
+                const float2 a0 = *reinterpret_cast<const float2*>(S.As + k * kRC + tr * 2);
+                av[0] = a0.x; av[1 % RM] = a0.y;
+            } else {
+                av[0] = S.As[k * kRC + tr];
+            }
+            const float4 b0 = *reinterpret_cast<const float4*>(S.Bs + k * kNB + tcg * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(S.Bs + k * kNB + tcg * 8 + 4);
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+    }
+    // ---- W[r, j0 + c] -= acc
+#pragma unroll
+    for (int i = 0; i < RM; ++i) {
+        const int rl = RM == 8 ? (i < 4 ? tr * 4 + i : 256 + tr * 4 + (i - 4)) : tr * RM + i;
+        const int r = r0 + rl;
+        if (r < nf) {
+            float* w = W + (size_t)r * ldw + j0 + tcg * 8;
+            float4 w0 = *reinterpret_cast<float4*>(w), w1 = *reinterpret_cast<float4*>(w + 4);
+            w0.x -= acc[i][0]; w0.y -= acc[i][1]; w0.z -= acc[i][2]; w0.w -= acc[i][3];
+            w1.x -= acc[i][4]; w1.y -= acc[i][5]; w1.z -= acc[i][6]; w1.w -= acc[i][7];
+            *reinterpret_cast<float4*>(w) = w0; *reinterpret_cast<float4*>(w + 4) = w1;
+        }
+    }
+}
+
 // Blocked left-looking Cholesky of the nf x nf lower triangle in W (row stride ldw): W <- L.
 __device__ void chol_blocked(float* __restrict__ W, int ldw, int nf, float floor_, const DenseSmem& S, int tid) {
     constexpr int LD = kNB + 1;
-    const int tr = tid & 63, tcg = tid >> 6;            // micro-tile: rows tr*8.., columns tcg*8..
     for (int j0 = 0; j0 < nf; j0 += kNB) {
         const int nb = nf - j0 < kNB ? nf - j0 : kNB;
-        for (int r0 = j0; r0 < nf; r0 += kRC) {
+        for (int r0 = j0; r0 < nf;) {
+            const int rem = nf - r0;
+            const int rows = rem > 256 ? 512 : (rem > 128 ? 256 : (rem > 64 ? 128 : 64));      // rows of this chunk
             if (j0 > 0) {
-                // ---- acc = sum_{p < j0} L[r0 + ., p] L[j0 + ., p]^T  for the chunk's 512 rows x 64 columns
-                float acc[8][8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
-                const int myrow = r0 + tid < nf ? r0 + tid : nf - 1;            // staging: one row per thread (clamped)
-                const int mybrow = j0 + (tid & 63) < nf ? j0 + (tid & 63) : nf - 1;
-                const float* arow = W + (size_t)myrow * ldw;
-                const float* brow = W + (size_t)mybrow * ldw;
-                float4 pa[4], pb[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    pa[u] = *reinterpret_cast<const float4*>(arow + u * 4);
-                    pb[u] = tid < 64 ? *reinterpret_cast<const float4*>(brow + u * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                for (int p0 = 0; p0 < j0; p0 += kKS) {
-                    __syncthreads();                    // previous slab consumed
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        S.As[(u * 4 + 0) * kRC + tid] = pa[u].x; S.As[(u * 4 + 1) * kRC + tid] = pa[u].y;
-                        S.As[(u * 4 + 2) * kRC + tid] = pa[u].z; S.As[(u * 4 + 3) * kRC + tid] = pa[u].w;
-                        if (tid < 64) {
-                            S.Bs[(u * 4 + 0) * kNB + tid] = pb[u].x; S.Bs[(u * 4 + 1) * kNB + tid] = pb[u].y;
-                            S.Bs[(u * 4 + 2) * kNB + tid] = pb[u].z; S.Bs[(u * 4 + 3) * kNB + tid] = pb[u].w;
-                        }
-                    }
-                    __syncthreads();
-                    if (p0 + kKS < j0) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            pa[u] = *reinterpret_cast<const float4*>(arow + p0 + kKS + u * 4);
-                            if (tid < 64) pb[u] = *reinterpret_cast<const float4*>(brow + p0 + kKS + u * 4);
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < kKS; ++k) {
-                        const float4 a0 = *reinterpret_cast<const float4*>(S.As + k * kRC + tr * 8);
-                        const float4 a1 = *reinterpret_cast<const float4*>(S.As + k * kRC + tr * 8 + 4);
-                        const float4 b0 = *reinterpret_cast<const float4*>(S.Bs + k * kNB + tcg * 8);
-                        const float4 b1 = *reinterpret_cast<const float4*>(S.Bs + k * kNB + tcg * 8 + 4);
-                        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-                    }
-                }
-                // ---- W[r, j0 + c] -= acc
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = r0 + tr * 8 + i;
-                    if (r < nf) {
-                        float* w = W + (size_t)r * ldw + j0 + tcg * 8;
-                        float4 w0 = *reinterpret_cast<float4*>(w), w1 = *reinterpret_cast<float4*>(w + 4);
-                        w0.x -= acc[i][0]; w0.y -= acc[i][1]; w0.z -= acc[i][2]; w0.w -= acc[i][3];
-                        w1.x -= acc[i][4]; w1.y -= acc[i][5]; w1.z -= acc[i][6]; w1.w -= acc[i][7];
-                        *reinterpret_cast<float4*>(w) = w0; *reinterpret_cast<float4*>(w + 4) = w1;
-                    }
-                }
+                if (rows == 512) chol_update_chunk<8>(W, ldw, nf, j0, r0, S, tid);
+                else if (rows == 256) chol_update_chunk<4>(W, ldw, nf, j0, r0, S, tid);
+                else if (rows == 128) chol_update_chunk<2>(W, ldw, nf, j0, r0, S, tid);
+                else chol_update_chunk<1>(W, ldw, nf, j0, r0, S, tid);
             }
             __syncthreads();
             if (r0 == j0) {
@@ -212,7 +242,7 @@ __device__ void chol_blocked(float* __restrict__ W, int ldw, int nf, float floor
             // ---- rows below the diagonal block: x <- x L_jj^-T, one row per thread
             {
                 const int r = r0 + tid;
-                if (r >= j0 + kNB && r < nf) {
+                if (tid < rows && r >= j0 + kNB && r < nf) {
                     float* w = W + (size_t)r * ldw + j0;
                     float x[kNB];
 #pragma unroll
@@ -237,6 +267,7 @@ __device__ void chol_blocked(float* __restrict__ W, int ldw, int nf, float floor
                 }
             }
             __syncthreads();
+            r0 += rows;
         }
     }
 }
@@ -316,16 +347,23 @@ __device__ void chol_solve_blocked(const float* __restrict__ W, int ldw, int nf,
     }
 }
 
-// gt = G lamt - bb over all m rows (one warp per row, float64 accumulation); returns lamt^T gt and bb^T lamt
+// gt = G lamt - bb over all m rows (one warp per row, float64 accumulation); returns lamt^T gt and bb^T lamt.
+// Four 16-byte loads per lane are issued before they are consumed (the rows come from L2 / HBM).
 __device__ void gram_matvec(const float* __restrict__ G, int ldg, int m, const double* lamt, const double* bb, double* gt,
                             Ctx& cx, double& lg, double& lb) {
     double a_lg = 0.0, a_lb = 0.0;
     for (int v = cx.warp; v < m; v += cx.nwarp) {
         const float* row = G + (size_t)v * ldg;
         double s = 0.0;
-        for (int j = cx.lane * 4; j < m; j += 128) {        // columns up to the next multiple of 128 are zero in G and in lamt
-            const float4 g4 = *reinterpret_cast<const float4*>(row + j);
-            s += (double)g4.x * lamt[j] + (double)g4.y * lamt[j + 1] + (double)g4.z * lamt[j + 2] + (double)g4.w * lamt[j + 3];
+        for (int j0 = cx.lane * 4; j0 < m; j0 += 512) {     // columns up to the next multiple of 128 are zero in G and in lamt
+            float4 g4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) g4[u] = j0 + u * 128 < m ? __ldg(reinterpret_cast<const float4*>(row + j0 + u * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * 128;
+                if (j < m) s += (double)g4[u].x * lamt[j] + (double)g4[u].y * lamt[j + 1] + (double)g4[u].z * lamt[j + 2] + (double)g4[u].w * lamt[j + 3];
+            }
         }
         s = cx.warp_sum(s);
         const double gv = s - bb[v];
@@ -357,11 +395,12 @@ __device__ double true_residual(const float* __restrict__ Ainst, int d, int m, c
     for (int k = cx.tid; k < d; k += cx.nthr) {
         double acc = (double)c[k];
         int i = 0;
-        for (; i + 4 <= ns; i += 4) {
-            const int v0 = S.sup[i], v1 = S.sup[i + 1], v2 = S.sup[i + 2], v3 = S.sup[i + 3];
-            const float a0 = __ldg(Ainst + (size_t)S.arow[v0] * d + k), a1 = __ldg(Ainst + (size_t)S.arow[v1] * d + k);
-            const float a2 = __ldg(Ainst + (size_t)S.arow[v2] * d + k), a3 = __ldg(Ainst + (size_t)S.arow[v3] * d + k);
-            acc -= x[v0] * (double)a0; acc -= x[v1] * (double)a1; acc -= x[v2] * (double)a2; acc -= x[v3] * (double)a3;
+        for (; i + 8 <= ns; i += 8) {                       // eight rows in flight per thread
+            float a[8]; double xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int v = S.sup[i + u]; a[u] = __ldg(Ainst + (size_t)S.arow[v] * d + k); xv[u] = x[v]; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc -= xv[u] * (double)a[u];
         }
         for (; i < ns; ++i) { const int v = S.sup[i]; acc -= x[v] * (double)__ldg(Ainst + (size_t)S.arow[v] * d + k); }
         rout[k] = acc; ff += acc * acc;
@@ -389,12 +428,26 @@ __device__ double kkt_residual(const double* lam, const double* g, int m, Ctx& c
     return cx.block_max(res);
 }
 
+// Coarse phase clocks (thread 0, clock64 deltas summed over instances): only in -DCAVE_DENSE_PROFILE builds.
+#ifdef CAVE_DENSE_PROFILE
+#define DPROF_BEGIN() long long dprof_t = clock64()
+#define DPROF(ph) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(prof + (ph), (unsigned long long)(t_ - dprof_t)); dprof_t = t_; } } while (0)
+#else
+#define DPROF_BEGIN() do {} while (0)
+#define DPROF(ph) do {} while (0)
+#endif
+enum { DP_SETUP = 0, DP_KKT = 1, DP_FREESET = 2, DP_GATHER = 3, DP_CHOL = 4, DP_TRISOLVE = 5, DP_LS_GRAM = 6, DP_LS_TRUE = 7,
+       DP_TRUEGRAD = 8, DP_EPILOGUE = 9, DP_SWITCH = 10, DP_NFACT = 11, DP_NITER = 12 };
+
 template <class TIO>
 __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
     extern __shared__ __align__(16) char dsm[];
     __shared__ double red[64];
     __shared__ int s_next, s_nf, s_same, s_cnt;
     int* ctrl = (int*)(p.ws + p.L.ctrl);
+#ifdef CAVE_DENSE_PROFILE
+    unsigned long long* prof = (unsigned long long*)(p.ws + p.L.ctrl + 64);
+#endif
     const int* list = (const int*)(p.ws + p.L.list);
     int* flag = (int*)(p.ws + p.L.flag);
     const int n_slots = (int)p.L.n_slots, mp = (int)p.L.m_pad;
@@ -428,6 +481,7 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
         const int s = s_next;
         __syncthreads();
         if (s >= n_round) break;
+        DPROF_BEGIN();
         const int b = list[p.round * n_slots + s];
         const size_t q = p.inst_index ? (size_t)p.inst_index[b] : (size_t)b;
         const int m = p.ngen[q], d = p.d;
@@ -456,6 +510,7 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
         cx.block_max2(l1m, dmax);
         const double cnorm = sqrt(cc);
         const bool finite_in = cc < 1e300;
+        DPROF(DP_SETUP);
         int status = ST_BADINPUT, iters = 0;
         bool handed_back = false;
         if (finite_in) {
@@ -464,7 +519,9 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
             const double tolG = 1e-6 * scale > tol ? 1e-6 * scale : tol;
             const int max_it1 = p.max_iter > 0 ? p.max_iter : 60, max_it2 = 24;
             const int max_ls = p.max_ls > 0 ? p.max_ls : 40;
-            const float regf = (float)(1e-6 * dmax), floorf_ = (float)(1e-7 * dmax);
+            // Tikhonov term above the accuracy of G~ (3xTF32 operands, truncating float32 accumulation: ~1.5e-5 relative on the
+            // diagonal at d = 1225), so that the factored matrix is positive definite even where G_FF is singular (|F| > d)
+            const float regf = (float)(4e-5 * dmax), floorf_ = (float)(1e-6 * dmax);
             int nf_fact = -1;                           // size of the free set the factor in W belongs to (-1: none)
             double f = 0.0;                             // phase 1: q(lam);  phase 2: 1/2 ||r||^2
             int phase = 1, since_best = 0, it1 = 0, it2 = 0;
@@ -474,6 +531,7 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
             status = ST_ITER_CAP;
             for (;;) {
                 double res = kkt_residual(lam, g, m, cx);
+                DPROF(DP_KKT);
                 if (phase == 1 && (res <= tolG || it1 >= max_it1)) {
                     if (res > 1e-4 * scale) { handed_back = true; break; }       // the Gram-space iteration did not settle
                     // ---- switch to the true problem: r = c - A^T lam, g = -A r
@@ -481,6 +539,7 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
                     f = 0.5 * true_residual<TIO>(Ainst, d, m, lam, c, rc, S, cx, &s_cnt);
                     true_gradient(Ainst, d, m, rc, g, S, cx);
                     res = kkt_residual(lam, g, m, cx);
+                    DPROF(DP_SWITCH);
                 }
                 if (phase == 2) {
                     if (!(res > tol)) { status = ST_CONVERGED; break; }
@@ -518,18 +577,30 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
                 __syncthreads();
                 const int nf = s_nf;
                 const bool same = s_same != 0;
+                DPROF(DP_FREESET);
                 if (nf > 0) {
                     if (!same) {
                         // gather the free block: W[a][b'] = G[F[a]][F[b']] (b' <= a) + reg on the diagonal, then factor
                         for (int a = cx.warp; a < nf; a += cx.nwarp) {
                             const float* grow = G + (size_t)S.fl[a] * mp;
                             float* wrow = W + (size_t)a * mp;
-                            for (int bq = cx.lane; bq <= a; bq += 32) wrow[bq] = grow[S.fl[bq]] + (bq == a ? regf : 0.0f);
+                            for (int b0 = cx.lane; b0 <= a; b0 += 256) {        // eight gathers in flight per lane
+                                float gv[8];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) { const int bq = b0 + u * 32; gv[u] = bq <= a ? __ldg(grow + S.fl[bq]) : 0.0f; }
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) { const int bq = b0 + u * 32; if (bq <= a) wrow[bq] = gv[u] + (bq == a ? regf : 0.0f); }
+                            }
                         }
                         for (int a = tid; a < nf; a += kDT) S.flp[a] = S.fl[a];
                         __syncthreads();
+                        DPROF(DP_GATHER);
                         chol_blocked(W, mp, nf, floorf_, S, tid);
                         nf_fact = nf;
+                        DPROF(DP_CHOL);
+#ifdef CAVE_DENSE_PROFILE
+                        if (tid == 0) atomicAdd(prof + DP_NFACT, 1ull);
+#endif
                     }
                     for (int a = tid; a < nf; a += kDT) S.xs[a] = (float)g[S.fl[a]];
                     __syncthreads();
@@ -537,6 +608,10 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
                     for (int a = tid; a < nf; a += kDT) S.dir[S.fl[a]] = (double)S.xs[a];
                 }
                 __syncthreads();
+                DPROF(DP_TRISOLVE);
+#ifdef CAVE_DENSE_PROFILE
+                if (tid == 0) atomicAdd(prof + DP_NITER, 1ull);
+#endif
                 // ---- Armijo along the projection arc
                 double alpha = 1.0, ft = f;
                 bool ok = false, at_floor = false;
@@ -552,8 +627,10 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
                         double lg, lb;
                         gram_matvec(G, mp, m, lamt, S.bb, gt, cx, lg, lb);
                         ft = 0.5 * lg - 0.5 * lb;
+                        DPROF(DP_LS_GRAM);
                     } else {
                         ft = 0.5 * true_residual<TIO>(Ainst, d, m, lamt, c, rtr, S, cx, &s_cnt);
+                        DPROF(DP_LS_TRUE);
                     }
                     const double fa = fabs(f);
                     if (ls == 0 && fabs(dec) <= 16.0 * kEps * fa && fabs(ft - f) <= 16.0 * kEps * fa) { ok = true; at_floor = true; break; }
@@ -573,6 +650,7 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
                 else {
                     { double* t3 = rc; rc = rtr; rtr = t3; }
                     true_gradient(Ainst, d, m, rc, g, S, cx);
+                    DPROF(DP_TRUEGRAD);
                     if (at_floor) { status = ST_CONVERGED; break; }
                 }
                 __syncthreads();
@@ -598,6 +676,7 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
             if (tid == 0) { p.status[b] = status | ST_PATH_GRAM; p.iters[b] = iters; }
         }
         __syncthreads();
+        DPROF(DP_EPILOGUE);
     }
 }
 

@@ -42,9 +42,11 @@ __global__ void __launch_bounds__(1024) dense_list_kernel(DenseParams p) {
         const int b = b0 + threadIdx.x;
         bool take = false;
         if (b < p.B && p.mode != 2) {
-            const size_t q = p.inst_index ? (size_t)p.inst_index[b] : (size_t)b;
-            const int ng = p.ngen[q];
-            take = p.nsingc[q] == 0 && ng >= kDenseMinRows && p.nvalid[q] == ng && (p.force || ng <= p.d + p.d / 2);
+            const long long q = p.inst_index ? (long long)p.inst_index[b] : (long long)b;
+            if (q >= 0 && q < p.n_packed) {           // (out-of-range indices are reported by the general kernel)
+                const int ng = p.ngen[q];
+                take = p.nsingc[q] == 0 && ng >= kDenseMinRows && p.nvalid[q] == ng && (p.force || ng <= p.d + p.d / 2);
+            }
         }
         const unsigned m = __ballot_sync(0xffffffffu, take);
         if (lane == 0) wsum[warp] = __popc(m);
@@ -58,6 +60,7 @@ __global__ void __launch_bounds__(1024) dense_list_kernel(DenseParams p) {
         __syncthreads();
     }
     if (threadIdx.x == 0) { ctrl[0] = base_s; ctrl[1] = 0; ctrl[2] = 0; ctrl[3] = 0; }
+    if (threadIdx.x < 16) ((unsigned long long*)(ctrl + 16))[threadIdx.x] = 0ull;       // phase clocks of profile builds
 }
 
 cudaError_t launch_dense_list(const DenseParams& p, cudaStream_t stream) {

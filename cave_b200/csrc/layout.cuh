@@ -30,10 +30,35 @@ CAVE_HD size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 //               launch configuration is chosen from them on the device, without a host round trip
 //   okey[B], order[B]   per-instance cost estimate and the instances sorted by it, most expensive first: the order
 //               in which the solve kernel's persistent CTAs take them (shortens the drain at the end of the kernel)
+//   setup[B, setup_stride]   per-instance solver setup emitted once by the setup kernel (A_i is constant across epochs:
+//               SURVEY.md 7.2): +- merge result, the kept rows as int8 CSR and the CSC over variables, i.e. everything
+//               nw_setup would otherwise recompute in every call; see SetupBlock
 struct PackLayout {
-    size_t nvalid, navg, ngen, gennnz, nsingc, gen, ctype, avg, csrok, maxl1, maxl2, ghash, csr_col, csr_val, plan, okey, order, total;
-    int64_t dpad, cap_nnz;
+    size_t nvalid, navg, ngen, gennnz, nsingc, gen, ctype, avg, csrok, maxl1, maxl2, ghash, csr_col, csr_val, plan, okey, order, setup, total;
+    int64_t dpad, cap_nnz, setup_stride, setup_cap_v;
 };
+
+// Cached setup of one structured instance (integer-valued rows only: every shipped model).  Byte offsets inside the block:
+//   [0]   int32 header: valid, nv (variables after the +- merge), nnz (non-zeros kept), reserved...   (32 bytes)
+//   vfree u8[cap_v]      variable is sign-free (a merged +- pair)
+//   rptr  i32[cap_v + 1] CSR row pointers over variables
+//   cptr  i32[d + 1]     CSC column pointers
+//   rcol  u16[cap_z]  crow u16[cap_z]  rval i8[cap_z]  cval i8[cap_z]
+struct SetupBlock { size_t vfree, rptr, cptr, rcol, crow, rval, cval, total; };
+CAVE_HD int64_t setup_cap_v(int64_t m_max) { return m_max < 1024 ? m_max : 1024; }
+CAVE_HD SetupBlock make_setup_block(int64_t cap_v, int64_t cap_z, int64_t d) {
+    SetupBlock S;
+    size_t o = 32;
+    S.vfree = o; o = align_up(o + (size_t)cap_v, 16);
+    S.rptr = o;  o = align_up(o + (size_t)(cap_v + 1) * 4, 16);
+    S.cptr = o;  o = align_up(o + (size_t)(d + 1) * 4, 16);
+    S.rcol = o;  o = align_up(o + (size_t)cap_z * 2, 16);
+    S.crow = o;  o = align_up(o + (size_t)cap_z * 2, 16);
+    S.rval = o;  o = align_up(o + (size_t)cap_z, 16);
+    S.cval = o;  o = align_up(o + (size_t)cap_z, 16);
+    S.total = align_up(o, 256);
+    return S;
+}
 
 // per-instance capacity of the packed CSR: every shipped model (TSP/VRP/SP) fits; instances that do
 // not (dense general rows) are flagged and the solver reads their rows from A instead
@@ -64,6 +89,9 @@ CAVE_HD PackLayout make_pack_layout(int64_t B, int64_t m_max, int64_t d) {
     L.plan = o;   o = align_up(o + 64, 256);
     L.okey = o;   o = align_up(o + (size_t)B * 4, 256);
     L.order = o;  o = align_up(o + (size_t)B * 4, 256);
+    L.setup_cap_v = setup_cap_v(m_max);
+    L.setup_stride = (int64_t)make_setup_block(L.setup_cap_v, L.cap_nnz, d).total;
+    L.setup = o;  o = align_up(o + (size_t)B * (size_t)L.setup_stride, 256);
     L.total = o;
     return L;
 }

@@ -34,6 +34,9 @@ struct PlanParams {
     unsigned long long* plan;   // zeroed by the caller on the same stream
     int* okey;                  // [B] cost estimate per instance
     int* order;                 // [B] instances by descending cost (filled by the order kernel)
+    // setup kernel (cached per-instance solver setup, layout.cuh SetupBlock)
+    const uint16_t* csr_col; const float* csr_val; int64_t cap_nnz;
+    char* setup; int64_t setup_stride, setup_cap_v;
 };
 cudaError_t launch_plan(const PlanParams& p, cudaStream_t stream);
 

@@ -14,6 +14,7 @@ hand-written sm_100a kernels behind the C ABI of include/cave_b200.h.  No CPU fa
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 
 import torch
@@ -182,6 +183,8 @@ def cave_forward_backward(pred_cost: torch.Tensor, tight_ctrs: torch.Tensor, sig
         out["proj"], out["rnorm"] = proj, rnorm
     if want_status:
         out["status"], out["iters"], out["rnorm"] = status, iters, rnorm
+    if os.environ.get("CAVE_KEEP_SCRATCH"):       # diagnostics (tools/dense_profile.py reads the dense control block)
+        out["_scratch"], out["_opts"] = scratch, opts
     return out
 
 

@@ -97,6 +97,9 @@ typedef struct cave_limits {
 } cave_limits;
 
 int cave_abi_version(void);
+/* Kernels this library has launched in the calling process so far (every entry point counts its own launches);
+ * bench.py reports the difference over its timed region as `gpu_launches`. */
+unsigned long long cave_launch_count(void);
 const char* cave_last_error(void);
 int cave_get_limits(cave_limits* out);
 
@@ -113,6 +116,11 @@ int cave_pack_bytes(int64_t B, int64_t m_max, int64_t d, size_t* out);
 int cave_plan_offset(int64_t B, int64_t m_max, int64_t d, size_t* out);
 int cave_plan_choice(const uint64_t* plan_host, int64_t d, int io_dtype, int compute_dtype,
                      int* threads, int* ctas_per_sm, int* smem_bytes);
+
+/* Diagnostics for the dense path: offset inside the scratch buffer of its control block: int32[16] ([0] = number of
+ * instances of the last call that took the dense path), followed by uint64[16] phase clocks that only builds with
+ * -DCAVE_DENSE_PROFILE fill (tools/dense_profile.py). */
+int cave_dense_ctrl_offset(int64_t B, int64_t m_max, int64_t d, const cave_solver_opts* opts, size_t* out);
 
 /* Bytes of solver scratch (per-CTA sparse rows, Hessian, vectors, work counter). */
 int cave_scratch_bytes(int64_t B, int64_t m_max, int64_t d, int compute_dtype,

@@ -1,0 +1,122 @@
+"""GPU tests of the module-level contract that the reference's own tests exercise (test/test_func.py:285-292 calls
+``_get_projection`` directly; :216-227 checks seeded branch sequences): the two-step ``_get_projection`` methods
+against the oracle's targets, and a CaVE Hybrid (solve_ratio = 0.3, BASELINE.json configs[3]) multi-call sequence
+against the oracle driven by the same ``RandomState``."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cave_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+class _Model:
+    def __init__(self, sense):
+        self.modelSense = sense
+
+
+def _data(kind, B, seed, regime="near"):
+    from cave_b200 import synth
+    insts = synth.make_batch(kind, B, seed=seed)
+    return synth.densify(insts).numpy(), synth.predictions(insts, seed, regime)
+
+
+def test_get_projection_exact_and_inner_match_oracle_targets():
+    from cave_b200 import EPO, exactConeAlignedCosine, innerConeAlignedCosine
+    dev = torch.device("cuda:0")
+    ctrs, pred = _data("tsp20", 12, 5)
+    c = -pred.astype(np.float64)                       # signed cost (MINIMIZE)
+    ct, At = torch.tensor(c, device=dev), torch.tensor(ctrs, device=dev)
+    t_ref, _, _ = O.exact_target(c, ctrs.astype(np.float64), fp64=True)
+    t = exactConeAlignedCosine(_Model(EPO.MINIMIZE), solver="cuda")._get_projection(ct, At)
+    np.testing.assert_allclose(t.cpu().numpy(), t_ref, rtol=1e-5, atol=1e-7)
+    # inner, QP branch (solve_ratio = 1: the draw is consumed, the branch is always the projection)
+    t_ref, _, rn = O.inner_target(c, ctrs.astype(np.float64), 0.2, fp64=True)
+    mod = innerConeAlignedCosine(_Model(EPO.MINIMIZE), solver="cuda", inner_ratio=0.2, solve_ratio=1.0, seed=3)
+    np.testing.assert_allclose(mod._get_projection(ct, At).cpu().numpy(), t_ref, rtol=1e-5, atol=1e-7)
+    # an instance inside its cone is returned un-pushed (src/cave.py:218-219)
+    lam = np.random.default_rng(0).random(ctrs.shape[1])
+    c_in = (lam @ ctrs[0].astype(np.float64))[None]
+    t_in, _, rn_in = O.inner_target(c_in, ctrs[:1].astype(np.float64), 0.2, fp64=True)
+    assert rn_in[0] < 1e-7
+    got = mod._get_projection(torch.tensor(c_in, device=dev), At[:1]).cpu().numpy()
+    np.testing.assert_allclose(got, t_in, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(np.linalg.norm(got), 1.0, rtol=1e-6)            # normalised projection, no avg mixed in
+    # heuristic branch (solve_ratio = 0: uniform() > 0 always)
+    modh = innerConeAlignedCosine(_Model(EPO.MINIMIZE), solver="cuda", inner_ratio=0.2, solve_ratio=0.0, seed=3)
+    t_h = O.heuristic_target(c, ctrs.astype(np.float64), 0.2)
+    np.testing.assert_allclose(modh._get_projection(ct, At).cpu().numpy(), t_h, rtol=1e-5, atol=1e-6)
+
+
+def test_vrp20_hybrid_sequence_follows_the_seeded_branch_draws():
+    """configs[3]: CaVE Hybrid, solve_ratio = 0.3, ragged VRP-20 rows.  One host draw per forward call
+    (src/cave.py:201); the oracle replays the same RandomState, so every call must land on the same branch and
+    the same loss / gradient."""
+    from cave_b200 import EPO, innerConeAlignedCosine
+    dev = torch.device("cuda:0")
+    seed, ratio = 7, 0.3
+    mod = innerConeAlignedCosine(_Model(EPO.MINIMIZE), solver="cuda", inner_ratio=0.2, solve_ratio=ratio, seed=seed,
+                                 solver_kwargs={"precision": "fp64"})
+    rng = np.random.RandomState(seed)
+    branches = []
+    for call in range(10):
+        ctrs, pred = _data("vrp20", 16, 100 + call, "near" if call % 2 else "uniform")
+        mode = O.MODE_HEURISTIC if rng.uniform() > ratio else O.MODE_INNER
+        branches.append(mode)
+        ref = O.forward_backward(pred.astype(np.float64), ctrs, mode=mode, inner_ratio=0.2, fp64=True)
+        p = torch.tensor(pred.astype(np.float64), device=dev, requires_grad=True)
+        loss = mod(p, torch.tensor(ctrs, device=dev))
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), ref["loss"], rtol=1e-5, atol=1e-8)
+        np.testing.assert_allclose(p.grad.cpu().numpy(), ref["grad"], rtol=1e-5, atol=1e-5 * np.abs(ref["grad"]).max())
+    assert O.MODE_HEURISTIC in branches and O.MODE_INNER in branches       # the sequence exercised both
+
+
+def test_pack_must_belong_to_the_tensor_and_index_is_range_checked():
+    """a warm pack reused for another same-shape batch must raise, and an out-of-range dataset index
+    must be reported (status + NaN), never read out of bounds."""
+    from cave_b200 import _lib, cave_forward_backward, pack_constraints
+    dev = torch.device("cuda:0")
+    ctrs, pred = _data("tsp20", 8, 1)
+    A = torch.tensor(ctrs, device=dev)
+    pk = pack_constraints(A)
+    p = torch.tensor(pred, device=dev)
+    cave_forward_backward(p, A, -1.0, 1, pack=pk)
+    with pytest.raises(ValueError):
+        cave_forward_backward(p, A.clone(), -1.0, 1, pack=pk)
+    A2 = A.clone()
+    pk2 = pack_constraints(A2)
+    A2[0, 0, 0] = 5.0
+    with pytest.raises(ValueError):
+        cave_forward_backward(p, A2, -1.0, 1, pack=pk2)
+    idx = torch.tensor([0, 3, 8, -1, 7, 2 ** 31 - 1], dtype=torch.int64, device=dev)
+    out = cave_forward_backward(p[:6], None, -1.0, 1, 0.2, "none", pack=pk, index=idx, want_status=True)
+    st = (out["status"] & 0xff).cpu().tolist()
+    assert st[2] == _lib.ST_BADINPUT and st[3] == _lib.ST_BADINPUT and st[5] == _lib.ST_BADINPUT
+    assert st[0] == 0 and st[1] == 0 and st[4] == 0
+    assert bool(torch.isnan(out["grad"][2]).all()) and bool(torch.isfinite(out["grad"][[0, 1, 4]]).all())
+
+
+def test_strict_mode_raises_on_unconverged_instances():
+    from cave_b200 import EPO, innerConeAlignedCosine
+    dev = torch.device("cuda:0")
+    ctrs, pred = _data("tsp20", 4, 2)
+    mod = innerConeAlignedCosine(_Model(EPO.MINIMIZE), solver="cuda", seed=0, solver_kwargs={"strict": True, "max_iter": 1})
+    with pytest.raises(RuntimeError):
+        mod(torch.tensor(pred, device=dev), torch.tensor(ctrs, device=dev))
+    ok = innerConeAlignedCosine(_Model(EPO.MINIMIZE), solver="cuda", seed=0, solver_kwargs={"strict": True})
+    assert torch.isfinite(ok(torch.tensor(pred, device=dev), torch.tensor(ctrs, device=dev)))
+
+
+def test_two_devices_in_one_process():
+    """kernel attributes and the SM count are per device, not per process."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from cave_b200 import cave_forward_backward
+    ctrs, pred = _data("tsp50", 2, 4)
+    outs = []
+    for i in (0, 1):
+        dev = torch.device("cuda", i)
+        outs.append(cave_forward_backward(torch.tensor(pred, device=dev), torch.tensor(ctrs, device=dev), -1.0, 1)["grad"].cpu())
+    assert torch.equal(outs[0], outs[1])

@@ -198,8 +198,10 @@ int cave_pack(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, i
     pp.nvalid = p.nvalid; pp.ngen = p.ngen; pp.gennnz = p.gennnz; pp.nsingc = p.nsingc; pp.csr_ok = p.csr_ok;
     pp.gen4 = p.gen4; pp.ghash = p.ghash; pp.plan = (unsigned long long*)(base + L.plan);
     pp.okey = (int*)(base + L.okey); pp.order = (int*)(base + L.order);
+    pp.csr_col = p.csr_col; pp.csr_val = p.csr_val; pp.cap_nnz = L.cap_nnz;
+    pp.setup = base + L.setup; pp.setup_stride = L.setup_stride; pp.setup_cap_v = L.setup_cap_v;
     e = cave::launch_plan(pp, (cudaStream_t)stream);
-    g_launches += 2;
+    g_launches += 3;
     if (e != cudaSuccess) return fail(CAVE_ECUDA, "plan kernel launch failed: %s", cudaGetErrorString(e));
     return CAVE_OK;
 }
@@ -268,6 +270,13 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     sp.plan = (const unsigned long long*)(pb + PL.plan);
     sp.order = (indexed || env_int("CAVE_SOLVE_ORDER", 1) == 0) ? nullptr : (const int*)(pb + PL.order);       // the order of a dataset-wide pack does not apply to a batch
     sp.n_packed = Bpack;
+    {
+        const cave::SetupBlock SBk = cave::make_setup_block(PL.setup_cap_v, PL.cap_nnz, d);
+        sp.setup = env_int("CAVE_SETUP_CACHE", 1) ? pb + PL.setup : nullptr;
+        sp.setup_stride = PL.setup_stride;
+        sp.sb_vfree = (unsigned)SBk.vfree; sp.sb_rptr = (unsigned)SBk.rptr; sp.sb_cptr = (unsigned)SBk.cptr; sp.sb_rcol = (unsigned)SBk.rcol;
+        sp.sb_crow = (unsigned)SBk.crow; sp.sb_rval = (unsigned)SBk.rval; sp.sb_cval = (unsigned)SBk.cval;
+    }
     sp.dense_flag = nullptr;
     if (dense) {
         // Dense regime first: instance list, then per round of n_slots instances the TF32 split, the tensor-core Gram and

@@ -347,27 +347,40 @@ __device__ void chol_solve_blocked(const float* __restrict__ W, int ldw, int nf,
     }
 }
 
-// gt = G lamt - bb over all m rows (one warp per row, float64 accumulation); returns lamt^T gt and bb^T lamt.
-// Four 16-byte loads per lane are issued before they are consumed (the rows come from L2 / HBM).
+// gt = G lamt - bb over all m rows (float64 accumulation); returns lamt^T gt and bb^T lamt.  The rows come from L2 / HBM with
+// a latency of microseconds under load, so every warp keeps two rows = up to sixteen 16-byte loads per lane in flight.
 __device__ void gram_matvec(const float* __restrict__ G, int ldg, int m, const double* lamt, const double* bb, double* gt,
                             Ctx& cx, double& lg, double& lb) {
     double a_lg = 0.0, a_lb = 0.0;
-    for (int v = cx.warp; v < m; v += cx.nwarp) {
-        const float* row = G + (size_t)v * ldg;
-        double s = 0.0;
-        for (int j0 = cx.lane * 4; j0 < m; j0 += 512) {     // columns up to the next multiple of 128 are zero in G and in lamt
-            float4 g4[4];
+    for (int v0 = 2 * cx.warp; v0 < m; v0 += 2 * cx.nwarp) {
+        const bool two = v0 + 1 < m;
+        const float* row0 = G + (size_t)v0 * ldg;
+        const float* row1 = G + (size_t)(two ? v0 + 1 : v0) * ldg;
+        double s0 = 0.0, s1 = 0.0;
+        for (int j0 = cx.lane * 4; j0 < m; j0 += 1024) {    // columns up to the next multiple of 128 are zero in G and in lamt
+            float4 g0[8], g1[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) g4[u] = j0 + u * 128 < m ? __ldg(reinterpret_cast<const float4*>(row + j0 + u * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int u = 0; u < 8; ++u) {
+                const bool in = j0 + u * 128 < m;
+                g0[u] = in ? __ldg(reinterpret_cast<const float4*>(row0 + j0 + u * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                g1[u] = in ? __ldg(reinterpret_cast<const float4*>(row1 + j0 + u * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const int j = j0 + u * 128;
-                if (j < m) s += (double)g4[u].x * lamt[j] + (double)g4[u].y * lamt[j + 1] + (double)g4[u].z * lamt[j + 2] + (double)g4[u].w * lamt[j + 3];
+                if (j < m) {
+                    const double l0 = lamt[j], l1 = lamt[j + 1], l2 = lamt[j + 2], l3 = lamt[j + 3];
+                    s0 += (double)g0[u].x * l0 + (double)g0[u].y * l1 + (double)g0[u].z * l2 + (double)g0[u].w * l3;
+                    s1 += (double)g1[u].x * l0 + (double)g1[u].y * l1 + (double)g1[u].z * l2 + (double)g1[u].w * l3;
+                }
             }
         }
-        s = cx.warp_sum(s);
-        const double gv = s - bb[v];
-        if (cx.lane == 0) { gt[v] = gv; a_lg += lamt[v] * gv; a_lb += bb[v] * lamt[v]; }
+        s0 = cx.warp_sum(s0); s1 = cx.warp_sum(s1);
+        if (cx.lane == 0) {
+            const double gv0 = s0 - bb[v0];
+            gt[v0] = gv0; a_lg += lamt[v0] * gv0; a_lb += bb[v0] * lamt[v0];
+            if (two) { const double gv1 = s1 - bb[v0 + 1]; gt[v0 + 1] = gv1; a_lg += lamt[v0 + 1] * gv1; a_lb += bb[v0 + 1] * lamt[v0 + 1]; }
+        }
     }
     cx.block_sum2(a_lg, a_lb);
     lg = a_lg; lb = a_lb;
@@ -395,12 +408,19 @@ __device__ double true_residual(const float* __restrict__ Ainst, int d, int m, c
     for (int k = cx.tid; k < d; k += cx.nthr) {
         double acc = (double)c[k];
         int i = 0;
-        for (; i + 8 <= ns; i += 8) {                       // eight rows in flight per thread
-            float a[8]; double xv[8];
+        for (; i + 32 <= ns; i += 32) {                     // 32 rows in flight per thread (the rows come from L2 / HBM)
+            float a[32];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { const int v = S.sup[i + u]; a[u] = __ldg(Ainst + (size_t)S.arow[v] * d + k); xv[u] = x[v]; }
+            for (int u = 0; u < 32; ++u) a[u] = __ldg(Ainst + (size_t)S.arow[S.sup[i + u]] * d + k);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) acc -= xv[u] * (double)a[u];
+            for (int u = 0; u < 32; ++u) acc -= x[S.sup[i + u]] * (double)a[u];
+        }
+        for (; i + 8 <= ns; i += 8) {
+            float a[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] = __ldg(Ainst + (size_t)S.arow[S.sup[i + u]] * d + k);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc -= x[S.sup[i + u]] * (double)a[u];
         }
         for (; i < ns; ++i) { const int v = S.sup[i]; acc -= x[v] * (double)__ldg(Ainst + (size_t)S.arow[v] * d + k); }
         rout[k] = acc; ff += acc * acc;
@@ -408,11 +428,20 @@ __device__ double true_residual(const float* __restrict__ Ainst, int d, int m, c
     return cx.block_sum(ff);        // (barriers inside: rout is visible afterwards)
 }
 
-// g = -A r over all rows (one warp per row)
+// g = -A r over all rows (one warp per row, sixteen 4-byte loads in flight per lane)
 __device__ void true_gradient(const float* __restrict__ Ainst, int d, int m, const double* r, double* g, const DenseSmem& S, Ctx& cx) {
     for (int v = cx.warp; v < m; v += cx.nwarp) {
-        const double w = row_dot<double>(cx, Ainst + (size_t)S.arow[v] * d, r, d);
-        if (cx.lane == 0) g[v] = -w;
+        const float* row = Ainst + (size_t)S.arow[v] * d;
+        double acc = 0.0;
+        for (int k0 = 0; k0 < d; k0 += 512) {
+            float a[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { const int k = k0 + u * 32 + cx.lane; a[u] = k < d ? __ldg(row + k) : 0.f; }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { const int k = k0 + u * 32 + cx.lane; if (k < d) acc += (double)a[u] * r[k]; }
+        }
+        acc = cx.warp_sum(acc);
+        if (cx.lane == 0) g[v] = -acc;
     }
     __syncthreads();
 }
@@ -670,7 +699,7 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
             Instance in;
             in.A = Ainst; in.gen = (const gen_t*)gen; in.ctype = p.ctype + q * p.dpad; in.avg = p.avg + q * p.dpad;
             in.d = d; in.ngen = m; in.gen_nnz = 0; in.nvalid = m; in.nsingc = 0; in.csr_ok = 0;
-            in.ghash = nullptr; in.pcol = nullptr; in.pval = nullptr; in.maxl1 = 0.f; in.maxl2 = 0.f;
+            in.ghash = nullptr; in.pcol = nullptr; in.pval = nullptr; in.maxl1 = 0.f; in.maxl2 = 0.f; in.setup = nullptr;
             epilogue<double, TIO, const TIO*>(cx, in, ep, c, r, p.mode != MODE_HEURISTIC, false, grad_all + (size_t)b * d,
                                               proj_all ? proj_all + (size_t)b * d : nullptr, p.loss64 + b, p.rnorm64 + b);
             if (tid == 0) { p.status[b] = status | ST_PATH_GRAM; p.iters[b] = iters; }

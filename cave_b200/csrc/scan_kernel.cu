@@ -677,11 +677,166 @@ __global__ void __launch_bounds__(256) order_kernel(PlanParams p) {
     if (lane == 0) p.order[rank] = b;
 }
 
+// ---- setup kernel: the per-instance setup of the Newton path, computed ONCE per pack (A_i is constant across epochs,
+// SURVEY.md 7.2) instead of in every solve: +- merge of the general rows (hash match + exact comparison), the kept rows
+// as int8 CSR over variables, and the CSC (count, scan, cursor fill, per-column sort by variable => fixed summation
+// order).  One CTA per instance; results go to the instance's SetupBlock in the pack (layout.cuh); the solver's
+// nw_setup turns into a copy-in.  Only integer-valued instances with a complete packed CSR are cached (every shipped
+// model); the others keep the in-solver setup.
+constexpr int kSetupThreads = 128;
+__host__ __device__ inline size_t setup_smem_bytes(int64_t cap_v, int64_t d) {
+    return (size_t)cap_v * (8 + 8 + 4 + 4 + 4 + 4 + 1) + 64 + (size_t)(d + 2) * 8 + 64;
+}
+__global__ void __launch_bounds__(kSetupThreads) setup_kernel(PlanParams p, int enabled) {
+    extern __shared__ __align__(16) char ssm[];
+    __shared__ int s_nv, s_nz;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kSetupThreads / 32;
+    char* blk = p.setup + (size_t)b * p.setup_stride;
+    int* hdr = (int*)blk;
+    const int mB = p.ngen[b], d = p.d;
+    const bool eligible = enabled && p.nsingc[b] > 0 && mB > 0 && (p.csr_ok[b] & 3) == 3 && mB <= p.setup_cap_v && p.nvalid[b] > 0;
+    if (!eligible) { if (tid == 0) hdr[0] = 0; return; }
+    const SetupBlock SB = make_setup_block(p.setup_cap_v, p.cap_nnz, d);
+    const int cv = (int)p.setup_cap_v;
+    unsigned long long* hpos = (unsigned long long*)ssm;
+    unsigned long long* hneg = hpos + cv;
+    int* goff = (int*)(hneg + cv);
+    int* gcnt = goff + cv + 1;
+    int* cand = gcnt + cv + 1;          // later: row pointers over variables
+    int* keep = cand + cv + 2;          // variable -> general row
+    int* cnt = keep + cv + 1;           // [d + 2] column counts / pointers
+    int* cur = cnt + d + 2;             // [d + 1] fill cursors
+    unsigned char* rtype = (unsigned char*)(cur + d + 1);
+    const int4* gen = p.gen4 + (size_t)b * p.m_max;
+    const ulonglong2* gh = p.ghash + (size_t)b * p.m_max;
+    const uint16_t* pcol = p.csr_col + (size_t)b * p.cap_nnz;
+    const float* pval = p.csr_val + (size_t)b * p.cap_nnz;
+    for (int i = tid; i < mB; i += kSetupThreads) {
+        const int4 g = gen[i]; gcnt[i] = g.y; goff[i] = g.z;
+        const ulonglong2 h = gh[g.x]; hpos[i] = h.x; hneg[i] = h.y;
+    }
+    for (int k = tid; k <= d + 1; k += kSetupThreads) cnt[k] = 0;
+    __syncthreads();
+    // merge b_j = -b_i: cand[i] = smallest j != i with row_j == -row_i; merged iff the choice is mutual
+    for (int i = warp; i < mB; i += NW) {
+        const int pi = goff[i], ni = gcnt[i];
+        const unsigned long long want = hneg[i];
+        int c0 = -1;
+        for (int j0 = 0; j0 < mB && c0 < 0; j0 += 32) {
+            const int j = j0 + lane;
+            const bool hit = j < mB && j != i && hpos[j] == want && gcnt[j] == ni;
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m && c0 < 0) {
+                const int jj = j0 + __ffs(m) - 1;
+                const int pj = goff[jj];
+                bool ok = true;
+                for (int e = lane; e < ni; e += 32) ok = ok & (pcol[pi + e] == pcol[pj + e]) & (pval[pi + e] == -pval[pj + e]);
+                if (!__ballot_sync(0xffffffffu, !ok)) c0 = jj;
+                m &= m - 1;
+            }
+        }
+        if (lane == 0) cand[i] = c0;
+    }
+    __syncthreads();
+    for (int i = tid; i < mB; i += kSetupThreads) {
+        const int j = cand[i];
+        rtype[i] = (j >= 0 && cand[j] == i) ? (i < j ? 1 : 2) : 0;
+    }
+    __syncthreads();
+    unsigned char* o_vfree = (unsigned char*)(blk + SB.vfree);
+    int* o_rptr = (int*)(blk + SB.rptr);
+    int* o_cptr = (int*)(blk + SB.cptr);
+    uint16_t* o_rcol = (uint16_t*)(blk + SB.rcol);
+    uint16_t* o_crow = (uint16_t*)(blk + SB.crow);
+    signed char* o_rval = (signed char*)(blk + SB.rval);
+    signed char* o_cval = (signed char*)(blk + SB.cval);
+    int* rp = cand;                     // reused: row pointers over variables
+    if (warp == 0) {                    // ordered compaction of the kept rows + exclusive scan of their lengths
+        int nvb = 0, run = 0;
+        for (int i0 = 0; i0 < mB; i0 += 32) {
+            const int i = i0 + lane;
+            const bool kp = i < mB && rtype[i] != 2;
+            const unsigned m = __ballot_sync(0xffffffffu, kp);
+            int len = kp ? gcnt[i] : 0, incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+            if (kp) {
+                const int v = nvb + __popc(m & ((1u << lane) - 1u));
+                keep[v] = i; o_vfree[v] = (unsigned char)(rtype[i] == 1);
+                const int start = run + incl - len;
+                rp[v] = start; o_rptr[v] = start;
+            }
+            nvb += __popc(m);
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) { rp[nvb] = run; o_rptr[nvb] = run; s_nv = nvb; s_nz = run; }
+    }
+    __syncthreads();
+    const int nv = s_nv, nz = s_nz;
+    // kept rows -> int8 CSR of the block; column counts
+    for (int v = warp; v < nv; v += NW) {
+        const int src = goff[keep[v]], dst = rp[v], n = rp[v + 1] - dst;
+        for (int e = lane; e < n; e += 32) {
+            const uint16_t c = pcol[src + e];
+            o_rcol[dst + e] = c; o_rval[dst + e] = (signed char)pval[src + e];
+            atomicAdd(&cnt[c + 1], 1);
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {                    // inclusive scan of cnt[1..d]: cnt[k] becomes the column pointer
+        int carry = 0;
+        for (int k0 = 1; k0 <= d; k0 += 32) {
+            const int k = k0 + lane;
+            int v = k <= d ? cnt[k] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+            v += carry;
+            if (k <= d) cnt[k] = v;
+            carry = __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k <= d; k += kSetupThreads) { o_cptr[k] = cnt[k]; if (k < d) cur[k] = cnt[k]; }
+    __syncthreads();
+    for (int v = warp; v < nv; v += NW) {
+        const int src = goff[keep[v]], n = rp[v + 1] - rp[v];
+        for (int e = lane; e < n; e += 32) {
+            const int q = atomicAdd(&cur[pcol[src + e]], 1);
+            o_crow[q] = (uint16_t)v; o_cval[q] = (signed char)pval[src + e];
+        }
+    }
+    __syncthreads();                    // (global writes of this CTA are visible to it after the barrier)
+    for (int k = tid; k < d; k += kSetupThreads) {          // insertion sort of every short column: deterministic order
+        const int s0 = cnt[k], e0 = cnt[k + 1];
+        if (e0 - s0 <= 64)
+            for (int a = s0 + 1; a < e0; ++a) {
+                const uint16_t rr = o_crow[a]; const signed char vv = o_cval[a];
+                int q = a - 1;
+                while (q >= s0 && o_crow[q] > rr) { o_crow[q + 1] = o_crow[q]; o_cval[q + 1] = o_cval[q]; --q; }
+                o_crow[q + 1] = rr; o_cval[q + 1] = vv;
+            }
+    }
+    if (tid == 0) { hdr[1] = nv; hdr[2] = nz; hdr[0] = 1; }
+}
+
 cudaError_t launch_plan(const PlanParams& p, cudaStream_t stream) {
     plan_kernel<<<dim3((unsigned)((p.B + 7) / 8)), dim3(256), 0, stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     order_kernel<<<dim3((unsigned)((p.B + 7) / 8)), dim3(256), 0, stream>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess || !p.setup) return e;
+    const size_t smem = setup_smem_bytes(p.setup_cap_v, p.d);
+    const char* off = getenv("CAVE_SETUP_CACHE");
+    const int enabled = (smem <= 200 * 1024 && !(off && off[0] == '0')) ? 1 : 0;
+    const size_t use = enabled ? smem : 0;
+    if (use > 48 * 1024) {
+        e = cudaFuncSetAttribute(setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)use);
+        if (e != cudaSuccess) return e;
+    }
+    setup_kernel<<<dim3((unsigned)p.B), dim3(kSetupThreads), use, stream>>>(p, enabled);
     return cudaGetLastError();
 }
 

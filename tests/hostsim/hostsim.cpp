@@ -61,6 +61,7 @@ static void run(const float* A, int B, int m, int d, const double* pred, double 
         bool all8 = true; for (float v : pk.val) all8 = all8 && v == (float)(int)v && fabsf(v) <= 127.f;
         in.csr_ok = (force_path & 2) ? 0 : (all8 ? 3 : 1);                                  // bit 1: rebuild the CSR from A
         in.ghash = pk.ghash.data(); in.pcol = pk.col.data(); in.pval = pk.val.data(); in.maxl1 = pk.maxl1; in.maxl2 = pk.maxl2;
+        in.setup = nullptr;
         if (force_path & 1) in.nsingc = 0 == in.nsingc ? 1 : in.nsingc;       // bit 0: force the Newton path
         Ctx cx; EpiParams ep; ep.mode = mode; ep.inner_ratio = inner_ratio; ep.sign = sign; ep.gscale = gscale;
         SolveOpts opt; opt.max_iter = 0; opt.max_ls = 0; opt.tol = 0;

@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from ._pyepo_compat import EPO, optModule
-from .qpsolver import CavePack, cave_forward_backward, project_cuda
+from .qpsolver import CavePack, SparseConstraints, cave_forward_backward, project_cuda
 
 _REFERENCE_SOLVERS = ("apgd", "clarabel", "nnls")
 # constructor-level solver_kwargs: properties of the solver, never of one particular batch (a pack, an index or a row-count
@@ -34,7 +34,7 @@ class _CaveCudaFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pred_cost, tight_ctrs, sign, mode, inner_ratio, reduction, kwargs):
-        if isinstance(tight_ctrs, CavePack):      # device-resident dataset: kwargs carries index=
+        if isinstance(tight_ctrs, CavePack):      # device-resident dataset: kwargs carries index= (or the pack is the batch)
             kwargs = dict(kwargs, pack=tight_ctrs)
             tight_ctrs = None
         strict = bool(kwargs.get("strict", False))

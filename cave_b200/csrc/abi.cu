@@ -171,9 +171,10 @@ int cave_scratch_bytes(int64_t B, int64_t m_max, int64_t d, int compute_dtype, c
     return CAVE_OK;
 }
 
-int cave_pack(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, int64_t d, void* pack, size_t pack_bytes,
-              void* stream) {
-    if (!A || !pack) return fail(CAVE_EINVAL, "A and pack must not be null");
+struct SparseIn { const long long* inst_off; const long long* row_ptr; const int* col; const float* val; };
+static int pack_impl(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, int64_t d, void* pack, size_t pack_bytes,
+                     void* stream, bool emit_setup, const SparseIn* sparse = nullptr) {
+    if ((!A && !sparse) || !pack) return fail(CAVE_EINVAL, "A and pack must not be null");
     if (int e = check_shape(B, m_max, d)) return e;
     const cave::PackLayout L = cave::make_pack_layout(B, m_max, d);
     if (pack_bytes < L.total) return fail(CAVE_ENOSPC, "pack buffer has %zu bytes, %zu needed", pack_bytes, L.total);
@@ -189,7 +190,8 @@ int cave_pack(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, i
     p.cap_nnz = (int)L.cap_nnz; p.csr_ok = (int*)(base + L.csrok); p.maxl1 = (float*)(base + L.maxl1); p.maxl2 = (float*)(base + L.maxl2);
     cudaError_t e = cudaMemsetAsync(base + L.plan, 0, 64, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(CAVE_ECUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
-    e = cave::launch_scan(p, (cudaStream_t)stream);
+    e = sparse ? cave::launch_scan_sparse(p, sparse->inst_off, sparse->row_ptr, sparse->col, sparse->val, (cudaStream_t)stream)
+               : cave::launch_scan(p, (cudaStream_t)stream);
     g_launches += 1;
     if (e != cudaSuccess) return fail(CAVE_ECUDA, "scan kernel launch failed: %s", cudaGetErrorString(e));
     cave::PlanParams pp;
@@ -199,11 +201,26 @@ int cave_pack(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, i
     pp.gen4 = p.gen4; pp.ghash = p.ghash; pp.plan = (unsigned long long*)(base + L.plan);
     pp.okey = (int*)(base + L.okey); pp.order = (int*)(base + L.order);
     pp.csr_col = p.csr_col; pp.csr_val = p.csr_val; pp.cap_nnz = L.cap_nnz;
-    pp.setup = base + L.setup; pp.setup_stride = L.setup_stride; pp.setup_cap_v = L.setup_cap_v;
+    // the cached solver setup pays off when the pack is reused (warm / dataset packs: cave_pack); a pack that lives for one
+    // call (cold cave_forward_backward) keeps the in-solver setup: the setup kernel would cost what it saves
+    pp.setup = emit_setup ? base + L.setup : nullptr; pp.setup_stride = L.setup_stride; pp.setup_cap_v = L.setup_cap_v;
     e = cave::launch_plan(pp, (cudaStream_t)stream);
-    g_launches += 3;
+    g_launches += emit_setup ? 3 : 2;
     if (e != cudaSuccess) return fail(CAVE_ECUDA, "plan kernel launch failed: %s", cudaGetErrorString(e));
     return CAVE_OK;
+}
+
+int cave_pack(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, int64_t d, void* pack, size_t pack_bytes,
+              void* stream) {
+    return pack_impl(A, m_rows, B, m_max, d, pack, pack_bytes, stream, true);
+}
+
+int cave_pack_sparse(const int64_t* inst_off, const int64_t* row_ptr, const int32_t* col, const float* val, int64_t B,
+                     int64_t m_max, int64_t d, int32_t flags, void* pack, size_t pack_bytes, void* stream) {
+    if (!inst_off || !row_ptr || !col || !val) return fail(CAVE_EINVAL, "inst_off, row_ptr, col and val must not be null");
+    SparseIn in;
+    in.inst_off = (const long long*)inst_off; in.row_ptr = (const long long*)row_ptr; in.col = col; in.val = val;
+    return pack_impl(nullptr, nullptr, B, m_max, d, pack, pack_bytes, stream, (flags & 1) != 0, &in);
 }
 
 int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pred, int64_t B, int64_t m_max, int64_t d,
@@ -243,7 +260,7 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
 
     cudaStream_t st = (cudaStream_t)stream;
     if (!(opts && opts->warm_pack)) {
-        if (int e = cave_pack(A, m_rows, B, m_max, d, pack, pack_bytes, stream)) return e;
+        if (int e = pack_impl(A, m_rows, B, m_max, d, pack, pack_bytes, stream, false)) return e;
     }
     char* pb = (char*)pack;
     char* sb = (char*)scratch;
@@ -270,13 +287,8 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     sp.plan = (const unsigned long long*)(pb + PL.plan);
     sp.order = (indexed || env_int("CAVE_SOLVE_ORDER", 1) == 0) ? nullptr : (const int*)(pb + PL.order);       // the order of a dataset-wide pack does not apply to a batch
     sp.n_packed = Bpack;
-    {
-        const cave::SetupBlock SBk = cave::make_setup_block(PL.setup_cap_v, PL.cap_nnz, d);
-        sp.setup = env_int("CAVE_SETUP_CACHE", 1) ? pb + PL.setup : nullptr;
-        sp.setup_stride = PL.setup_stride;
-        sp.sb_vfree = (unsigned)SBk.vfree; sp.sb_rptr = (unsigned)SBk.rptr; sp.sb_cptr = (unsigned)SBk.cptr; sp.sb_rcol = (unsigned)SBk.rcol;
-        sp.sb_crow = (unsigned)SBk.crow; sp.sb_rval = (unsigned)SBk.rval; sp.sb_cval = (unsigned)SBk.cval;
-    }
+    sp.setup = (opts && opts->warm_pack && env_int("CAVE_SETUP_CACHE", 1)) ? pb + PL.setup : nullptr;
+    sp.setup_stride = PL.setup_stride;
     sp.dense_flag = nullptr;
     if (dense) {
         // Dense regime first: instance list, then per round of n_slots instances the TF32 split, the tensor-core Gram and

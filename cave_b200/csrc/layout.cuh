@@ -39,16 +39,19 @@ struct PackLayout {
 };
 
 // Cached setup of one structured instance (integer-valued rows only: every shipped model).  Byte offsets inside the block:
-//   [0]   int32 header: valid, nv (variables after the +- merge), nnz (non-zeros kept), reserved...   (32 bytes)
+//   [0]   int32 header: valid, nv (variables after the +- merge), nnz (non-zeros kept), then the byte offsets of the
+//         seven arrays below (64 bytes)
 //   vfree u8[cap_v]      variable is sign-free (a merged +- pair)
 //   rptr  i32[cap_v + 1] CSR row pointers over variables
 //   cptr  i32[d + 1]     CSC column pointers
 //   rcol  u16[cap_z]  crow u16[cap_z]  rval i8[cap_z]  cval i8[cap_z]
 struct SetupBlock { size_t vfree, rptr, cptr, rcol, crow, rval, cval, total; };
-CAVE_HD int64_t setup_cap_v(int64_t m_max) { return m_max < 1024 ? m_max : 1024; }
+// instances with more general rows than this keep the in-solver setup (every shipped model has far fewer: TSP-50 ~110,
+// TSP-100 ~210); a small cap keeps the setup kernel's shared memory small, i.e. many instances in flight per SM
+CAVE_HD int64_t setup_cap_v(int64_t m_max) { return m_max < 256 ? m_max : 256; }
 CAVE_HD SetupBlock make_setup_block(int64_t cap_v, int64_t cap_z, int64_t d) {
     SetupBlock S;
-    size_t o = 32;
+    size_t o = 64;
     S.vfree = o; o = align_up(o + (size_t)cap_v, 16);
     S.rptr = o;  o = align_up(o + (size_t)(cap_v + 1) * 4, 16);
     S.cptr = o;  o = align_up(o + (size_t)(d + 1) * 4, 16);

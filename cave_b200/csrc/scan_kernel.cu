@@ -606,6 +606,185 @@ cudaError_t launch_scan(const ScanParams& p0, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sparse ingestion: the same pack, built from the non-zeros of the rows (CSR per instance) instead of the dense
+// [B, m_max, d] tensor — 90 KB instead of 6.5 MB per TSP-50 instance cross PCIe / HBM.  Row classification, thresholds,
+// the 2^-40 fixed-point average, hashes and the packed CSR are those of scan_rows_kernel (for integer-valued rows the
+// pack content is identical; for other values the row norms may differ in the last bit: different summation order).
+// One CTA per instance, one warp per row.  Columns inside a row must be ascending; explicit zeros are skipped.
+struct SparseScanParams {
+    const long long* inst_off;      // [B + 1] first row of every instance in row_ptr
+    const long long* row_ptr;       // [R + 1]
+    const int* col; const float* val;
+    ScanParams pk;                  // pack pointers (A unused)
+};
+constexpr int kSparseThreads = 256;
+__host__ __device__ inline size_t sparse_scan_smem_bytes(int d, int m_max, int64_t dpad) {
+    return (size_t)d * 12 + 16 + (size_t)m_max * 8 + 64 + 16 * 4 + 2 * (kSparseThreads / 32) * 4 + 16 + (size_t)dpad + 64;
+}
+__global__ void __launch_bounds__(kSparseThreads) scan_sparse_kernel(SparseScanParams q) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const ScanParams& p = q.pk;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NT = kSparseThreads, NW = NT / 32;
+    const int d = p.d, b = blockIdx.x;
+    unsigned long long* avg_fx = (unsigned long long*)smem;                          // [d]
+    int* sing = (int*)(avg_fx + d);                                                  // [d]
+    int2* rowinfo = (int2*)align_up((size_t)(sing + d), 8);                         // [m_max]
+    int* s_cnt = (int*)(rowinfo + p.m_max);                                         // [16 + NW]
+    float* s_max = (float*)(s_cnt + 16 + NW);                                       // [2 * NW]
+    unsigned* ctype_w = (unsigned*)align_up((size_t)(s_max + 2 * NW), 16);          // [dpad / 4]
+    const long long r_first = q.inst_off[b];
+    long long nrows = q.inst_off[b + 1] - r_first;
+    const int m_b = (int)(nrows < 0 ? 0 : (nrows > p.m_max ? p.m_max : nrows));
+    for (int k = tid; k < d; k += NT) { avg_fx[k] = 0ull; sing[k] = 0; }
+    for (int k = tid; k < (int)(p.dpad / 4); k += NT) ctype_w[k] = 0u;
+    for (int k = tid; k < p.m_max; k += NT) rowinfo[k] = make_int2(0, 0);
+    if (tid < 16 + NW) s_cnt[tid] = 0;
+    __syncthreads();
+    int w_nvalid = 0, w_navg = 0, w_gennnz = 0, w_ngen = 0;
+    float w_l1max = 0.f, w_l2max = 0.f;
+    uint16_t* col_out = p.csr_col + (size_t)b * p.cap_nnz;
+    float* val_out = p.csr_val + (size_t)b * p.cap_nnz;
+    ulonglong2* hash_out = p.ghash + (size_t)b * p.m_max;
+    for (int row_id = warp; row_id < m_b; row_id += NW) {
+        const long long e0 = q.row_ptr[r_first + row_id], e1 = q.row_ptr[r_first + row_id + 1];
+        RowAcc acc; acc.l1 = 0.f; acc.l2 = 0.f; acc.lv = 0.f; acc.lk = -1; acc.n = 0;
+        for (long long e = e0 + lane; e < e1; e += 32) {
+            const float v = q.val[e];
+            const int k = q.col[e];
+            if (v != 0.f && k >= 0 && k < d) acc.add(v, k);
+        }
+        int cnt = acc.n;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        const unsigned sawm = __ballot_sync(0xffffffffu, acc.n > 0);
+        if (cnt == 1) {
+            const int src = __ffs(sawm) - 1;
+            const int k1 = __shfl_sync(0xffffffffu, acc.lk, src);
+            const float v1 = __shfl_sync(0xffffffffu, acc.lv, src);
+            const bool nv = fabsf(v1) > 1e-7f, av = sqrtf(v1 * v1) > 1e-7f;
+            w_nvalid += nv; w_navg += av;
+            if (lane == 0) {
+                if (nv) atomicOr(&ctype_w[k1 >> 2], (v1 > 0.f ? 1u : 2u) << ((k1 & 3) * 8));
+                if (av) atomicAdd(&sing[k1], v1 > 0.f ? 1 : -1);
+            }
+        } else if (cnt >= 2) {
+            float a1 = acc.l1, a2 = acc.l2;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+            const float nrm = sqrtf(a2);
+            const bool nv = a1 > 1e-7f, av = nrm > 1e-7f;
+            const float inv = av ? 1.f / fmaxf(nrm, 1e-8f) : 0.f;
+            w_nvalid += nv; w_navg += av;
+            int off = 0;
+            bool fits = false;
+            if (nv) {
+                if (lane == 0) off = atomicAdd(&s_cnt[5], cnt);
+                off = __shfl_sync(0xffffffffu, off, 0);
+                fits = off + cnt <= p.cap_nnz;
+                if (!fits && lane == 0) s_cnt[6] = 1;
+                w_gennnz += cnt; ++w_ngen;
+                w_l1max = fmaxf(w_l1max, a1); w_l2max = fmaxf(w_l2max, a2);
+            }
+            uint64_t hp = 0, hn = 0;
+            int w = off;
+            for (long long eb = e0; eb < e1; eb += 32) {
+                const long long e = eb + lane;
+                float v = 0.f; int k = 0;
+                if (e < e1) { v = q.val[e]; k = q.col[e]; if (k < 0 || k >= d) v = 0.f; }
+                const unsigned nzm = __ballot_sync(0xffffffffu, v != 0.f);
+                if (v != 0.f) {
+                    if (av) atomicAdd(&avg_fx[k], (unsigned long long)__double2ll_rn((double)v * (double)inv * 1099511627776.0));
+                    if (fits) {
+                        const int pos = w + __popc(nzm & ((1u << lane) - 1u));
+                        col_out[pos] = (uint16_t)k; val_out[pos] = v;
+                        if (!(v == (float)(int)v && fabsf(v) <= 127.f)) s_cnt[7] = 1;
+                        const uint32_t bits = __float_as_uint(v);
+                        hp += mix64d(((uint64_t)k << 32) | bits);
+                        hn += mix64d(((uint64_t)k << 32) | (bits ^ 0x80000000u));
+                    }
+                }
+                w += __popc(nzm);
+            }
+            if (nv) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { hp += __shfl_xor_sync(0xffffffffu, hp, o); hn += __shfl_xor_sync(0xffffffffu, hn, o); }
+                if (lane == 0) { rowinfo[row_id] = make_int2(cnt, off); hash_out[row_id] = make_ulonglong2(hp, hn); }
+            }
+        }
+        __syncwarp();
+    }
+    // ---- once per instance: totals and the ordered general-row list (as in scan_rows_kernel)
+    if (lane == 0) {
+        atomicAdd(&s_cnt[0], w_nvalid); atomicAdd(&s_cnt[1], w_navg);
+        atomicAdd(&s_cnt[2], w_ngen); atomicAdd(&s_cnt[3], w_gennnz);
+        s_max[warp] = w_l1max; s_max[NW + warp] = w_l2max;
+    }
+    __syncthreads();
+    {
+        const int chunk = (p.m_max + NW - 1) / NW;
+        const int r0 = warp * chunk, r1 = min(r0 + chunk, p.m_max);
+        int mine = 0;
+        for (int r = r0 + lane; r < r1 + lane; r += 32) {
+            const bool g = r < r1 && rowinfo[r].x > 0;
+            mine += __popc(__ballot_sync(0xffffffffu, g));
+        }
+        if (lane == 0) s_cnt[16 + warp] = mine;
+        __syncthreads();
+        int basei = 0;
+        for (int w2 = 0; w2 < warp; ++w2) basei += s_cnt[16 + w2];
+        int4* gen_out = p.gen4 + (size_t)b * p.m_max;
+        for (int r = r0 + lane; r < r1 + lane; r += 32) {
+            const bool g = r < r1 && rowinfo[r].x > 0;
+            const unsigned m = __ballot_sync(0xffffffffu, g);
+            if (g) {
+                const int2 ri = rowinfo[r];
+                gen_out[basei + __popc(m & ((1u << lane) - 1u))] = make_int4(r, ri.x, ri.y, 0);
+            }
+            basei += __popc(m);
+        }
+    }
+    int nsc = 0;
+    for (int k = tid; k < (int)(p.dpad / 4); k += NT) {
+        const unsigned wv = ctype_w[k];
+        nsc += ((wv & 0xffu) != 0) + ((wv & 0xff00u) != 0) + ((wv & 0xff0000u) != 0) + ((wv & 0xff000000u) != 0);
+    }
+    for (int o = 16; o > 0; o >>= 1) nsc += __shfl_xor_sync(0xffffffffu, nsc, o);
+    if (lane == 0 && nsc) atomicAdd(&s_cnt[4], nsc);
+    __syncthreads();
+    const float ninv = 1.f / (float)max(s_cnt[1], 1);
+    float* avg_out = p.avg + (size_t)b * p.dpad;
+    for (int k = tid; k < (int)p.dpad; k += NT) {
+        float acc = 0.f;
+        if (k < d) acc = ((float)((double)(long long)avg_fx[k] * (1.0 / 1099511627776.0)) + (float)sing[k]) * ninv;
+        avg_out[k] = acc;
+    }
+    uint32_t* ct_out = (uint32_t*)(p.ctype + (size_t)b * p.dpad);
+    for (int k = tid; k < (int)(p.dpad / 4); k += NT) ct_out[k] = ctype_w[k];
+    if (tid == 0) {
+        float m1 = 0.f, m2 = 0.f;
+        for (int w2 = 0; w2 < NW; ++w2) { m1 = fmaxf(m1, s_max[w2]); m2 = fmaxf(m2, s_max[NW + w2]); }
+        p.nvalid[b] = s_cnt[0]; p.navg[b] = s_cnt[1]; p.ngen[b] = s_cnt[2]; p.gennnz[b] = s_cnt[3]; p.nsingc[b] = s_cnt[4];
+        p.csr_ok[b] = s_cnt[6] ? 0 : (s_cnt[7] ? 1 : 3);
+        p.maxl1[b] = m1; p.maxl2[b] = m2;
+    }
+}
+
+cudaError_t launch_scan_sparse(const ScanParams& pk, const long long* inst_off, const long long* row_ptr, const int* col,
+                               const float* val, cudaStream_t stream) {
+    SparseScanParams q;
+    q.inst_off = inst_off; q.row_ptr = row_ptr; q.col = col; q.val = val; q.pk = pk;
+    const size_t smem = sparse_scan_smem_bytes(pk.d, pk.m_max, pk.dpad);
+    if (smem > 220 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(scan_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    scan_sparse_kernel<<<dim3((unsigned)pk.B), dim3(kSparseThreads), smem, stream>>>(q);
+    return cudaGetLastError();
+}
+
 // ---- plan kernel: one warp per instance estimates the solver's shared-memory footprint (general rows, rows
 // that will merge into +- pairs by hash, non-zeros kept) and reduces it into the batch statistics from which
 // the solve kernel's launch configuration is chosen on the device (layout.cuh).  Integer sums and maxima:
@@ -818,7 +997,12 @@ __global__ void __launch_bounds__(kSetupThreads) setup_kernel(PlanParams p, int 
                 o_crow[q + 1] = rr; o_cval[q + 1] = vv;
             }
     }
-    if (tid == 0) { hdr[1] = nv; hdr[2] = nz; hdr[0] = 1; }
+    if (tid == 0) {
+        hdr[1] = nv; hdr[2] = nz;
+        hdr[3] = (int)SB.vfree; hdr[4] = (int)SB.rptr; hdr[5] = (int)SB.cptr; hdr[6] = (int)SB.rcol; hdr[7] = (int)SB.crow;
+        hdr[8] = (int)SB.rval; hdr[9] = (int)SB.cval;
+        hdr[0] = 1;
+    }
 }
 
 cudaError_t launch_plan(const PlanParams& p, cudaStream_t stream) {

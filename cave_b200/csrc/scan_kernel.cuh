@@ -25,6 +25,9 @@ struct ScanParams {
 };
 
 cudaError_t launch_scan(const ScanParams& p, cudaStream_t stream);
+// sparse ingestion: the same pack from per-instance CSR input (device pointers); p.A is unused
+cudaError_t launch_scan_sparse(const ScanParams& p, const long long* inst_off, const long long* row_ptr, const int* col,
+                               const float* val, cudaStream_t stream);
 
 struct PlanParams {
     int B, m_max, d;

@@ -44,7 +44,6 @@ struct SolveParams {
     long long n_packed;    // instances in the pack (inst_index values must be below it)
     const char* setup;     // nullable: cached per-instance setup blocks of the pack (layout.cuh SetupBlock)
     long long setup_stride;
-    unsigned sb_vfree, sb_rptr, sb_cptr, sb_rcol, sb_crow, sb_rval, sb_cval;
 };
 
 struct FinalizeParams {

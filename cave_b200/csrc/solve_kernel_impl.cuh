@@ -53,8 +53,6 @@ __global__ void __launch_bounds__(CAVE_LB_T, CAVE_LB_C) solve_kernel(SolveParams
         in.pcol = p.csr_col + q * p.cap_nnz;
         in.pval = p.csr_val + q * p.cap_nnz;
         in.setup = p.setup ? p.setup + q * (size_t)p.setup_stride : nullptr;
-        in.sb_vfree = p.sb_vfree; in.sb_rptr = p.sb_rptr; in.sb_cptr = p.sb_cptr; in.sb_rcol = p.sb_rcol; in.sb_crow = p.sb_crow;
-        in.sb_rval = p.sb_rval; in.sb_cval = p.sb_cval;
         solve_instance<T, TIO>(cx, in, smem, (size_t)p.smem_bytes, slot, p.slot_bytes, pred + (size_t)b * p.d, ep, opt, grad + (size_t)b * p.d,
                                proj ? proj + (size_t)b * p.d : nullptr, p.loss64 + b, p.rnorm64 + b,
                                p.status + b, p.iters + b);

@@ -111,6 +111,89 @@ def pack_constraints(tight_ctrs: torch.Tensor, m_rows: torch.Tensor | None = Non
     return CavePack(buf, (B, m, d), A.data_ptr(), A if keep_dense else None, int(tight_ctrs._version))
 
 
+@dataclass
+class SparseConstraints:
+    """Binding-constraint rows of a batch / dataset as per-instance CSR (host or device tensors):
+    rows ``[inst_off[b], inst_off[b+1])`` of ``row_ptr`` belong to instance ``b`` (the reference's row order,
+    src/dataset.py:178-211), row ``r`` holds ``col/val[row_ptr[r]:row_ptr[r+1]]`` with ascending columns.
+    The sparse counterpart of the padded ``[B, m_max, d]`` tensor of ``collate_fn`` (src/dataset.py:133-144): about
+    90 KB instead of 6.5 MB per TSP-50 instance."""
+    inst_off: torch.Tensor      # int64 [B + 1]
+    row_ptr: torch.Tensor       # int64 [R + 1]
+    col: torch.Tensor           # int32 [nnz]
+    val: torch.Tensor           # float32 [nnz]
+    m_max: int
+    d: int
+
+    @property
+    def batch(self) -> int:
+        return int(self.inst_off.numel() - 1)
+
+    def nbytes(self) -> int:
+        return int(sum(t.numel() * t.element_size() for t in (self.inst_off, self.row_ptr, self.col, self.val)))
+
+    @staticmethod
+    def from_dense(tight_ctrs: torch.Tensor) -> "SparseConstraints":
+        """Host-side conversion of a padded dense ``[B, m, d]`` tensor (all-zero rows are padding and are dropped)."""
+        import numpy as np
+        A = tight_ctrs.detach().cpu().numpy()
+        B, m, d = A.shape
+        inst_off, row_ptr, cols, vals = [0], [0], [], []
+        for b in range(B):
+            keep = np.flatnonzero(np.abs(A[b]).sum(axis=1) > 0)
+            for r in keep:
+                k = np.flatnonzero(A[b, r])
+                cols.append(k.astype(np.int32)); vals.append(A[b, r, k].astype(np.float32))
+                row_ptr.append(row_ptr[-1] + len(k))
+            inst_off.append(inst_off[-1] + len(keep))
+        return SparseConstraints(torch.tensor(inst_off, dtype=torch.int64), torch.tensor(row_ptr, dtype=torch.int64),
+                                 torch.from_numpy(np.concatenate(cols) if cols else np.zeros(0, np.int32)),
+                                 torch.from_numpy(np.concatenate(vals) if vals else np.zeros(0, np.float32)), m, d)
+
+    @staticmethod
+    def from_instances(insts, m_max: int | None = None) -> "SparseConstraints":
+        """From ``cave_b200.synth.SparseInstance`` objects (COO, rows in the reference's order)."""
+        import numpy as np
+        d = insts[0].d
+        m_max = max(i.m for i in insts) if m_max is None else m_max
+        inst_off = np.zeros(len(insts) + 1, np.int64)
+        ptrs, cols, vals = [np.zeros(1, np.int64)], [], []
+        base = 0
+        for b, it in enumerate(insts):
+            order = np.lexsort((it.cols, it.rows))
+            cnt = np.bincount(it.rows, minlength=it.m).astype(np.int64)
+            ptrs.append(base + np.cumsum(cnt)); base += int(cnt.sum())
+            cols.append(it.cols[order].astype(np.int32)); vals.append(it.vals[order].astype(np.float32))
+            inst_off[b + 1] = inst_off[b] + it.m
+        return SparseConstraints(torch.from_numpy(inst_off), torch.from_numpy(np.concatenate(ptrs)),
+                                 torch.from_numpy(np.concatenate(cols)), torch.from_numpy(np.concatenate(vals)), int(m_max), int(d))
+
+    def pin_memory(self) -> "SparseConstraints":
+        return SparseConstraints(self.inst_off.pin_memory(), self.row_ptr.pin_memory(), self.col.pin_memory(), self.val.pin_memory(),
+                                 self.m_max, self.d)
+
+
+def pack_constraints_sparse(sc: SparseConstraints, device=None, cache_setup: bool = True) -> CavePack:
+    """Builds the device-resident pack straight from per-instance CSR (``cave_pack_sparse``): no dense tensor exists on
+    the device, so instances that would need it (no singleton row at all, or general rows beyond the packed-CSR
+    capacity) report ``CAVE_ST_NOSPACE``.  Host tensors are uploaded on the current stream (pinned -> asynchronous)."""
+    lib = _lib.load()
+    dev = _device_of(sc.val, device)
+    B, m, d = sc.batch, int(sc.m_max), int(sc.d)
+    io = _to_device(sc.inst_off, dev, torch.int64)
+    rp = _to_device(sc.row_ptr, dev, torch.int64)
+    col = _to_device(sc.col, dev, torch.int32)
+    val = _to_device(sc.val, dev, torch.float32)
+    nbytes = ctypes.c_size_t()
+    _lib.check(lib.cave_pack_bytes(B, m, d, ctypes.byref(nbytes)))
+    buf = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.cave_pack_sparse(_ptr(io), _ptr(rp), _ptr(col), _ptr(val), B, m, d, 1 if cache_setup else 0,
+                                        _ptr(buf), nbytes.value, ctypes.c_void_p(stream)))
+    return CavePack(buf, (B, m, d), 0, None, 0)
+
+
 def cave_forward_backward(pred_cost: torch.Tensor, tight_ctrs: torch.Tensor, sign: float, mode: int,
                           inner_ratio: float = 0.2, reduction: str = "mean", precision: str = "fp64",
                           want_proj: bool = False, want_status: bool = False, pack: CavePack | None = None,
@@ -122,6 +205,11 @@ def cave_forward_backward(pred_cost: torch.Tensor, tight_ctrs: torch.Tensor, sig
     gradient of one), and optionally ``proj``, ``rnorm``, ``status``, ``iters`` — all on the
     compute device, in ``pred_cost``'s dtype."""
     lib = _lib.load()
+    if isinstance(tight_ctrs, SparseConstraints):      # one-shot sparse batch: pack from the non-zeros, then the indexed path
+        pack = pack_constraints_sparse(tight_ctrs, device=device, cache_setup=False)
+        tight_ctrs = None
+    if index is None and tight_ctrs is None and pack is not None and pack.shape[0] == pred_cost.shape[0]:
+        index = torch.arange(pred_cost.shape[0], dtype=torch.int32, device=pack.buf.device)     # the pack IS the batch
     if index is not None:
         return _forward_backward_indexed(lib, pred_cost, tight_ctrs, sign, mode, inner_ratio, reduction, precision,
                                          want_proj, want_status, pack, index, device, max_iter, max_linesearch, tol,

@@ -134,6 +134,18 @@ int cave_scratch_bytes(int64_t B, int64_t m_max, int64_t d, int compute_dtype,
 int cave_pack(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, int64_t d,
               void* pack, size_t pack_bytes, void* stream);
 
+/* Sparse ingestion: the same pack built from the non-zeros of the binding-constraint rows instead of the dense padded
+ * tensor (every shipped model is 0.7 % dense at TSP-50: 90 KB instead of 6.5 MB per instance cross PCIe and HBM).
+ * Replaces DataLoader + collate_fn's dense zero padding (src/dataset.py:114-144) for callers that keep `dataset.ctrs`
+ * sparse.  Device pointers: rows [inst_off[b], inst_off[b+1]) of row_ptr belong to instance b (at most m_max, in the
+ * reference's row order); row r holds the entries [row_ptr[r], row_ptr[r+1]) of col / val, columns ascending, explicit
+ * zeros ignored.  flags bit 0: also emit the cached solver setup (worth it when the pack is reused across steps).
+ * The pack is then used with opts->warm_pack (and opts->inst_index); A may be NULL in cave_forward_backward, in which
+ * case instances that need the dense rows (no singleton row at all, or general rows beyond the packed-CSR capacity)
+ * report CAVE_ST_NOSPACE. */
+int cave_pack_sparse(const int64_t* inst_off, const int64_t* row_ptr, const int32_t* col, const float* val, int64_t B,
+                     int64_t m_max, int64_t d, int32_t flags, void* pack, size_t pack_bytes, void* stream);
+
 /* The hot path.  pred: [B,d] predicted costs (io_dtype).  sign: -1 for EPO.MINIMIZE, +1 for
  * EPO.MAXIMIZE (src/cave.py:62-68).  Outputs (io_dtype unless noted; any of proj, rnorm,
  * status, iters, loss may be NULL):

@@ -120,3 +120,70 @@ def test_two_devices_in_one_process():
         dev = torch.device("cuda", i)
         outs.append(cave_forward_backward(torch.tensor(pred, device=dev), torch.tensor(ctrs, device=dev), -1.0, 1)["grad"].cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("kind,B", [("tsp20", 24), ("vrp20", 24), ("sp5", 16), ("tsp50", 3)])
+def test_sparse_ingestion_matches_the_dense_path_bitwise(kind, B):
+    """cave_pack_sparse (per-instance CSR in, no dense tensor on the device) must give the pack of the dense scan:
+    integer-valued rows => identical results, bit for bit, through the warm / indexed solve."""
+    from cave_b200 import SparseConstraints, cave_forward_backward, pack_constraints_sparse, synth
+    dev = torch.device("cuda:0")
+    insts = synth.make_batch(kind, B, seed=9)
+    A = synth.densify(insts, device=dev)
+    pred = torch.tensor(synth.predictions(insts, 9, "near"), device=dev, dtype=torch.float64)
+    ref = cave_forward_backward(pred, A, -1.0, 1, 0.2, "none", want_proj=True, want_status=True)
+    sc = SparseConstraints.from_instances(insts)
+    assert sc.nbytes() * 8 < A.numel() * 4
+    pk = pack_constraints_sparse(sc)
+    out = cave_forward_backward(pred, None, -1.0, 1, 0.2, "none", want_proj=True, want_status=True, pack=pk)
+    one = cave_forward_backward(pred, sc.pin_memory(), -1.0, 1, 0.2, "none", want_proj=True, want_status=True)    # one-shot from host CSR
+    for o in (out, one):
+        assert ((o["status"] & 0xff) == 0).all()
+        for k in ("loss_i", "grad", "proj", "rnorm"):
+            assert torch.equal(o[k], ref[k]), k
+    # a permuted index into the same pack
+    idx = torch.randperm(B, device=dev).to(torch.int32)
+    sub = cave_forward_backward(pred[idx.long()], None, -1.0, 1, 0.2, "none", pack=pk, index=idx)
+    assert torch.equal(sub["grad"], ref["grad"][idx.long()])
+
+
+def test_sparse_ingestion_float_rows_and_instances_that_need_the_dense_rows():
+    from cave_b200 import _lib, SparseConstraints, cave_forward_backward, pack_constraints_sparse
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(3)
+    B, m, d = 6, 40, 30
+    A = np.zeros((B, m, d), np.float32)
+    for b in range(B):
+        for r in range(12):                                     # general rows with float values
+            k = rng.choice(d, size=rng.integers(2, 6), replace=False)
+            A[b, r, k] = rng.standard_normal(len(k)).astype(np.float32)
+        for k in range(d):                                      # one singleton row per coordinate
+            A[b, 12 + k if 12 + k < m else m - 1, k] = rng.choice([-1.5, 2.0])
+    A[5, 12:] = 0                                               # instance 5: no singleton row -> needs the dense rows
+    At = torch.tensor(A, device=dev)
+    pred = torch.tensor(rng.standard_normal((B, d)), device=dev)
+    ref = cave_forward_backward(pred, At, -1.0, 0, reduction="none", want_proj=True, want_status=True)
+    pk = pack_constraints_sparse(SparseConstraints.from_dense(At))
+    out = cave_forward_backward(pred, None, -1.0, 0, reduction="none", want_proj=True, want_status=True, pack=pk)
+    st = (out["status"] & 0xff).cpu().tolist()
+    assert st[:5] == [0] * 5 and st[5] == _lib.ST_NOSPACE
+    np.testing.assert_allclose(out["proj"][:5].cpu().numpy(), ref["proj"][:5].cpu().numpy(), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(out["loss_i"][:5].cpu().numpy(), ref["loss_i"][:5].cpu().numpy(), rtol=1e-10, atol=1e-12)
+
+
+def test_module_accepts_sparse_constraints_and_packs():
+    from cave_b200 import EPO, SparseConstraints, innerConeAlignedCosine, pack_constraints_sparse, synth
+    dev = torch.device("cuda:0")
+    insts = synth.make_batch("tsp20", 8, seed=4)
+    A = synth.densify(insts, device=dev)
+    pred = synth.predictions(insts, 4, "near")
+    mod = innerConeAlignedCosine(_Model(EPO.MINIMIZE), solver="cuda", seed=0)
+    p0 = torch.tensor(pred, device=dev, requires_grad=True)
+    l0 = mod(p0, A); l0.backward()
+    sc = SparseConstraints.from_instances(insts)
+    p1 = torch.tensor(pred, requires_grad=True)                 # host prediction, host CSR
+    l1 = mod(p1, sc); l1.backward()
+    p2 = torch.tensor(pred, device=dev, requires_grad=True)
+    l2 = mod(p2, pack_constraints_sparse(sc)); l2.backward()
+    assert l1.device.type == "cpu" and float(l1) == float(l0) == float(l2)
+    assert torch.equal(p1.grad, p0.grad.cpu()) and torch.equal(p2.grad, p0.grad)

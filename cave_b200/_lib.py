@@ -17,7 +17,8 @@ ST_CONVERGED, ST_ITER_CAP, ST_STALLED, ST_NOSPACE, ST_SKIPPED, ST_BADINPUT, ST_P
 
 EXPORTS = ("cave_abi_version", "cave_last_error", "cave_get_limits", "cave_pack_bytes",
            "cave_scratch_bytes", "cave_pack", "cave_forward_backward", "cave_plan_offset", "cave_plan_choice",
-           "cave_dense_gram", "cave_launch_count", "cave_dense_ctrl_offset", "cave_pack_sparse")
+           "cave_dense_gram", "cave_launch_count", "cave_dense_ctrl_offset", "cave_pack_sparse",
+           "cave_tsp_scratch_bytes", "cave_tsp_solve")
 
 
 class SolverOpts(ctypes.Structure):
@@ -61,13 +62,16 @@ def load() -> ctypes.CDLL:
                                           ctypes.POINTER(SolverOpts), P, P, P, P, P, P, P,
                                           P, ctypes.c_size_t, P, ctypes.c_size_t, P]
     lib.cave_dense_gram.argtypes = [P, I64, I64, I64, ctypes.POINTER(SolverOpts), P, P, P, ctypes.c_size_t, P, ctypes.c_size_t, P]
+    lib.cave_tsp_scratch_bytes.argtypes = [I64, I32, SZP]
+    lib.cave_tsp_solve.argtypes = [P, I64, I32, P, P, P, ctypes.c_size_t, P]
     lib.cave_pack_sparse.argtypes = [P, P, P, P, I64, I64, I64, I32, P, ctypes.c_size_t, P]
     lib.cave_dense_ctrl_offset.argtypes = [I64, I64, I64, ctypes.POINTER(SolverOpts), SZP]
     lib.cave_plan_offset.argtypes = [I64, I64, I64, SZP]
     IP = ctypes.POINTER(ctypes.c_int)
     lib.cave_plan_choice.argtypes = [ctypes.POINTER(ctypes.c_uint64), I64, I32, I32, IP, IP, IP]
     for name in ("cave_get_limits", "cave_pack_bytes", "cave_scratch_bytes", "cave_pack", "cave_forward_backward",
-                 "cave_plan_offset", "cave_plan_choice", "cave_dense_gram", "cave_dense_ctrl_offset", "cave_pack_sparse"):
+                 "cave_plan_offset", "cave_plan_choice", "cave_dense_gram", "cave_dense_ctrl_offset", "cave_pack_sparse",
+           "cave_tsp_scratch_bytes", "cave_tsp_solve"):
         getattr(lib, name).restype = I32
     _lib = lib
     return lib

@@ -75,12 +75,41 @@ int check_shape(int64_t B, int64_t m_max, int64_t d) {
     return CAVE_OK;
 }
 
-void resolve_caps(const cave_solver_opts* o, int64_t m_max, int64_t d, int64_t* cap_rows, int64_t* cap_nnz) {
-    int64_t r = (o && o->cap_rows > 0) ? o->cap_rows : m_max;
+// Caps of the per-CTA ("small") slot.  Explicit caps keep their old meaning (instances beyond them report CAVE_ST_NOSPACE, no
+// worst-case slots).  By default the small slot is sized for structured instances (<= 192 general rows, non-zeros within the
+// packed-CSR capacity) and a few worst-case slots serve everything else.
+bool resolve_caps(const cave_solver_opts* o, int64_t m_max, int64_t d, int64_t* cap_rows, int64_t* cap_nnz) {
+    const bool explicit_caps = o && (o->cap_rows > 0 || o->cap_nnz > 0);
+    int64_t r = (o && o->cap_rows > 0) ? o->cap_rows : (explicit_caps ? m_max : (m_max < 192 ? m_max : 192));
     if (r > m_max) r = m_max;
-    int64_t z = (o && o->cap_nnz > 0) ? o->cap_nnz : r * d;
+    int64_t z = (o && o->cap_nnz > 0) ? o->cap_nnz : (explicit_caps ? r * d : cave::pack_cap_nnz(m_max, d));
     if (z > r * d) z = r * d;
     *cap_rows = r; *cap_nnz = z;
+    return explicit_caps;
+}
+
+struct ScratchPlan { int64_t cr, cz, n_slots, n_large; size_t large_bytes; };
+ScratchPlan plan_scratch(const cave_solver_opts* o, int64_t B, int64_t m_max, int64_t d);
+
+ScratchPlan plan_scratch(const cave_solver_opts* o, int64_t B, int64_t m_max, int64_t d) {
+    ScratchPlan P;
+    const bool explicit_caps = resolve_caps(o, m_max, d, &P.cr, &P.cz);
+    const size_t small = cave::solver_slot_bytes(d, P.cr, P.cz, 8);
+    P.n_slots = solver_slots(B, small);
+    P.n_large = 0; P.large_bytes = 0;
+    if (!explicit_caps) {
+        const size_t worst = cave::solver_slot_bytes(d, m_max, m_max * d, 8);
+        if (worst > small) {
+            // a 1 GiB scratch in total where that leaves at least 8 worst-case slots; never more than one per CTA of the 2/SM grid
+            const size_t used = small * (size_t)P.n_slots;
+            int64_t n = used < ((size_t)1 << 30) ? (int64_t)((((size_t)1 << 30) - used) / worst) : 0;
+            if (n < 8) n = 8;
+            if (n > cave::kMaxLargeSlots) n = cave::kMaxLargeSlots;
+            if (n > B) n = B;
+            P.n_large = n; P.large_bytes = worst;
+        }
+    }
+    return P;
 }
 
 // ---- dense (tensor-core Gram) path: host-side gate and workspace sizing
@@ -136,9 +165,8 @@ int cave_plan_offset(int64_t B, int64_t m_max, int64_t d, size_t* out) {
 int cave_dense_ctrl_offset(int64_t B, int64_t m_max, int64_t d, const cave_solver_opts* opts, size_t* out) {
     if (!out) return fail(CAVE_EINVAL, "out is null");
     if (int e = check_shape(B, m_max, d)) return e;
-    int64_t cr, cz;
-    resolve_caps(opts, m_max, d, &cr, &cz);
-    const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, cr, cz, 8, solver_slots(B, cave::solver_slot_bytes(d, cr, cz, 8)));
+    const ScratchPlan SPn = plan_scratch(opts, B, m_max, d);
+    const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, SPn.cr, SPn.cz, 8, SPn.n_slots, SPn.n_large, SPn.large_bytes);
     *out = cave::make_dense_layout(B, m_max, d, dense_slots(opts, B, m_max, d), SL.total).ctrl;
     return CAVE_OK;
 }
@@ -160,9 +188,8 @@ int cave_scratch_bytes(int64_t B, int64_t m_max, int64_t d, int compute_dtype, c
     if (!out) return fail(CAVE_EINVAL, "out is null");
     if (int e = check_shape(B, m_max, d)) return e;
     if (compute_dtype != CAVE_F32 && compute_dtype != CAVE_F64) return fail(CAVE_EINVAL, "bad compute_dtype %d", compute_dtype);
-    int64_t cr, cz;
-    resolve_caps(opts, m_max, d, &cr, &cz);
-    size_t total = cave::make_scratch_layout(B, d, cr, cz, 8, solver_slots(B, cave::solver_slot_bytes(d, cr, cz, 8))).total;
+    const ScratchPlan SPn = plan_scratch(opts, B, m_max, d);
+    size_t total = cave::make_scratch_layout(B, d, SPn.cr, SPn.cz, 8, SPn.n_slots, SPn.n_large, SPn.large_bytes).total;
     // mode and A are not known here: sized for the case that the call takes the dense path
     static const float kSomeA = 0.f;
     if (dense_enabled(opts, &kSomeA, m_max, d, CAVE_MODE_EXACT))
@@ -246,11 +273,10 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     if (int e = check_shape(Bpack, m_max, d)) return e;
     const cave::PackLayout PL = cave::make_pack_layout(Bpack, m_max, d);
     if (pack_bytes < PL.total) return fail(CAVE_ENOSPC, "pack buffer has %zu bytes, %zu needed", pack_bytes, PL.total);
-    int64_t cr, cz;
-    resolve_caps(opts, m_max, d, &cr, &cz);
+    const ScratchPlan SPn = plan_scratch(opts, B, m_max, d);
     const size_t T = 8;   // state vectors are double in both modes; sized for the f64 factor
-    const int64_t n_slots = solver_slots(B, cave::solver_slot_bytes(d, cr, cz, T));
-    const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, cr, cz, T, n_slots);
+    const int64_t n_slots = SPn.n_slots;
+    const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, SPn.cr, SPn.cz, T, n_slots, SPn.n_large, SPn.large_bytes);
     const bool dense = dense_enabled(opts, A, m_max, d, mode);
     cave::DenseLayout DL;
     memset(&DL, 0, sizeof(DL));
@@ -280,6 +306,7 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     sp.counter = (int*)(sb + SL.counter); sp.loss64 = (double*)(sb + SL.loss64); sp.rnorm64 = (double*)(sb + SL.rnorm64);
     sp.status = (int*)(sb + SL.status); sp.iters = (int*)(sb + SL.iters);
     sp.slots = sb + SL.slots; sp.slot_bytes = SL.slot_bytes;
+    sp.large = sb + SL.large; sp.large_bytes = SL.large_bytes; sp.n_large = (int)SL.n_large;
     sp.mode = mode; sp.inner_ratio = inner_ratio; sp.sign = sign;
     sp.gscale = reduction == CAVE_REDUCE_MEAN ? 1.0 / (double)B : 1.0;
     sp.max_iter = opts ? opts->max_iter : 0; sp.max_ls = opts ? opts->max_linesearch : 0; sp.tol = opts ? opts->tol : 0.0;
@@ -355,6 +382,32 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     return CAVE_OK;
 }
 
+namespace cave {
+size_t tsp_slot_floats(int n);
+cudaError_t launch_tsp(const float* cost, int N, int n, int* tour, double* obj, void* scratch, int n_slots, cudaStream_t stream);
+}
+
+int cave_tsp_scratch_bytes(int64_t N, int32_t n_nodes, size_t* out) {
+    if (!out) return fail(CAVE_EINVAL, "out is null");
+    if (N <= 0 || n_nodes < 3 || n_nodes > 20) return fail(CAVE_ELIMIT, "Held-Karp needs 3 <= n_nodes <= 20 and N > 0");
+    const int64_t slots = N < sm_count() ? N : sm_count();
+    *out = (size_t)slots * cave::tsp_slot_floats(n_nodes) * 4;
+    return CAVE_OK;
+}
+
+int cave_tsp_solve(const float* cost, int64_t N, int32_t n_nodes, int32_t* tour, double* obj, void* scratch, size_t scratch_bytes,
+                   void* stream) {
+    if (!cost || !tour || !obj || !scratch) return fail(CAVE_EINVAL, "cost, tour, obj and scratch must not be null");
+    size_t need = 0;
+    if (int e = cave_tsp_scratch_bytes(N, n_nodes, &need)) return e;
+    if (scratch_bytes < need) return fail(CAVE_ENOSPC, "scratch buffer has %zu bytes, %zu needed", scratch_bytes, need);
+    const int64_t slots = N < sm_count() ? N : sm_count();
+    cudaError_t ce = cave::launch_tsp(cost, (int)N, n_nodes, tour, obj, scratch, (int)slots, (cudaStream_t)stream);
+    g_launches += 1;
+    if (ce != cudaSuccess) return fail(CAVE_ECUDA, "Held-Karp kernel launch failed: %s", cudaGetErrorString(ce));
+    return CAVE_OK;
+}
+
 int cave_dense_gram(const float* A, int64_t B, int64_t m_max, int64_t d, const cave_solver_opts* opts, float* G_out,
                     int32_t* n_dense_out, void* pack, size_t pack_bytes, void* scratch, size_t scratch_bytes, void* stream) {
     if (!A || !G_out || !pack || !scratch) return fail(CAVE_EINVAL, "A, G_out, pack, scratch must not be null");
@@ -368,9 +421,8 @@ int cave_dense_gram(const float* A, int64_t B, int64_t m_max, int64_t d, const c
     if (!o.warm_pack) { if (int e = cave_pack(A, nullptr, B, m_max, d, pack, pack_bytes, stream)) return e; }
     const cave::PackLayout PL = cave::make_pack_layout(B, m_max, d);
     if (pack_bytes < PL.total) return fail(CAVE_ENOSPC, "pack buffer has %zu bytes, %zu needed", pack_bytes, PL.total);
-    int64_t cr, cz;
-    resolve_caps(&o, m_max, d, &cr, &cz);
-    const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, cr, cz, 8, solver_slots(B, cave::solver_slot_bytes(d, cr, cz, 8)));
+    const ScratchPlan SPn = plan_scratch(&o, B, m_max, d);
+    const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, SPn.cr, SPn.cz, 8, SPn.n_slots, SPn.n_large, SPn.large_bytes);
     const cave::DenseLayout DL = cave::make_dense_layout(B, m_max, d, dense_slots(&o, B, m_max, d), SL.total);
     if (scratch_bytes < DL.total) return fail(CAVE_ENOSPC, "scratch buffer has %zu bytes, %zu needed", scratch_bytes, DL.total);
     char* pb = (char*)pack;

@@ -147,10 +147,14 @@ CAVE_HD int choose_solve_config(const unsigned long long* plan, size_t th, size_
     return kNumSolveConfigs - 1;
 }
 
-// Solver scratch: [work counter][loss64 B][rnorm64 B][status B][iters B][one slot per CTA]
+// Solver scratch: [work counter + large-slot locks][loss64 B][rnorm64 B][status B][iters B][one small slot per CTA]
+// [n_large worst-case slots].  A CTA spills into its own small slot (sized for the structured instances every shipped model
+// produces); an instance whose working set cannot fit there takes one of the few worst-case slots under a device-side
+// lock for the duration of its solve (the holders never wait for anybody, so the waiters always get served).
+constexpr int kMaxLargeSlots = 48;
 struct ScratchLayout {
-    size_t counter, loss64, rnorm64, status, iters, slots, slot_bytes, total;
-    int64_t n_slots;
+    size_t counter, loss64, rnorm64, status, iters, slots, slot_bytes, large, large_bytes, total;
+    int64_t n_slots, n_large;
 };
 
 CAVE_HD size_t solver_slot_bytes(int64_t d, int64_t cap_rows, int64_t cap_nnz, size_t T) {
@@ -166,10 +170,10 @@ CAVE_HD size_t solver_slot_bytes(int64_t d, int64_t cap_rows, int64_t cap_nnz, s
 }
 
 CAVE_HD ScratchLayout make_scratch_layout(int64_t B, int64_t d, int64_t cap_rows, int64_t cap_nnz, size_t T,
-                                          int64_t n_slots) {
+                                          int64_t n_slots, int64_t n_large = 0, size_t large_bytes = 0) {
     ScratchLayout L;
     size_t o = 0;
-    L.counter = o; o = align_up(o + 256, 256);
+    L.counter = o; o = align_up(o + 256, 256);          // int[0] work counter, int[8 .. 8 + n_large) slot locks
     L.loss64 = o;  o = align_up(o + (size_t)B * 8, 256);
     L.rnorm64 = o; o = align_up(o + (size_t)B * 8, 256);
     L.status = o;  o = align_up(o + (size_t)B * 4, 256);
@@ -177,6 +181,8 @@ CAVE_HD ScratchLayout make_scratch_layout(int64_t B, int64_t d, int64_t cap_rows
     L.slot_bytes = solver_slot_bytes(d, cap_rows, cap_nnz, T);
     L.n_slots = n_slots;
     L.slots = o;   o += L.slot_bytes * (size_t)n_slots;
+    L.n_large = n_large; L.large_bytes = large_bytes;
+    L.large = o;   o += large_bytes * (size_t)n_large;
     L.total = o;
     return L;
 }

@@ -28,6 +28,7 @@ struct SolveParams {
     int *status, *iters;
     char* slots;
     size_t slot_bytes;
+    char* large; size_t large_bytes; int n_large;      // worst-case slots, taken under a lock (counter[8 + i]) when needed
     int smem_bytes;
     // epilogue / options
     int mode;

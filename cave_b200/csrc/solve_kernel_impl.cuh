@@ -17,7 +17,7 @@ template <class T, class TIO>
 __global__ void __launch_bounds__(CAVE_LB_T, CAVE_LB_C) solve_kernel(SolveParams p) {
     extern __shared__ __align__(16) char smem[];
     __shared__ double red[64];
-    __shared__ int s_b;
+    __shared__ int s_b, s_large;
     if (p.cfg_id >= 0 && choose_solve_config(p.plan, sizeof(T), sizeof(TIO) == 8 ? (size_t)p.d * 4 : 0) != p.cfg_id) return;
     Ctx cx(red);
     char* slot = p.slots + (size_t)blockIdx.x * p.slot_bytes;
@@ -53,10 +53,29 @@ __global__ void __launch_bounds__(CAVE_LB_T, CAVE_LB_C) solve_kernel(SolveParams
         in.pcol = p.csr_col + q * p.cap_nnz;
         in.pval = p.csr_val + q * p.cap_nnz;
         in.setup = p.setup ? p.setup + q * (size_t)p.setup_stride : nullptr;
-        solve_instance<T, TIO>(cx, in, smem, (size_t)p.smem_bytes, slot, p.slot_bytes, pred + (size_t)b * p.d, ep, opt, grad + (size_t)b * p.d,
+        // an instance whose working set cannot fit this CTA's slot borrows one of the worst-case slots under a lock
+        char* islot = slot; size_t islot_bytes = p.slot_bytes;
+        int held = -1;
+        if (p.n_large > 0 && in.ngen > 0 && solver_slot_bytes(p.d, in.ngen, in.gen_nnz, 8) > p.slot_bytes) {
+            if (cx.tid == 0) {
+                int got = -1;
+                unsigned ns = 64;
+                for (int probe = (int)(blockIdx.x % (unsigned)p.n_large); got < 0; probe = (probe + 1) % p.n_large) {
+                    if (atomicCAS(p.counter + 8 + probe, 0, 1) == 0) got = probe;
+                    else if (probe == (int)(blockIdx.x % (unsigned)p.n_large)) { __nanosleep(ns); ns = ns < 4096 ? ns * 2 : ns; }
+                }
+                __threadfence();
+                s_large = got;
+            }
+            __syncthreads();
+            held = s_large;
+            islot = p.large + (size_t)held * p.large_bytes; islot_bytes = p.large_bytes;
+        }
+        solve_instance<T, TIO>(cx, in, smem, (size_t)p.smem_bytes, islot, islot_bytes, pred + (size_t)b * p.d, ep, opt, grad + (size_t)b * p.d,
                                proj ? proj + (size_t)b * p.d : nullptr, p.loss64 + b, p.rnorm64 + b,
                                p.status + b, p.iters + b);
         __syncthreads();
+        if (held >= 0 && cx.tid == 0) { __threadfence(); atomicExch(p.counter + 8 + held, 0); }
     }
 }
 

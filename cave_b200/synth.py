@@ -68,11 +68,13 @@ def _assemble(d, blocks, sol) -> SparseInstance:
                           np.concatenate(vals), sol.astype(np.uint8))
 
 
-def tsp_instance(n: int, rng: np.random.Generator, max_cuts: int) -> SparseInstance:
-    """TSP-n DFJ: rows [D; -D; k tight subtour cuts; -e_k; +e_k], m = 2n + d + k."""
+def tsp_instance(n: int, rng: np.random.Generator, max_cuts: int, tour: np.ndarray | None = None) -> SparseInstance:
+    """TSP-n DFJ: rows [D; -D; k tight subtour cuts; -e_k; +e_k], m = 2n + d + k.  `tour`: the optimal tour the rows are
+    binding at (a random permutation when not given)."""
     d = n * (n - 1) // 2
     eidx = _edge_index(n)
-    tour = rng.permutation(n)
+    if tour is None:
+        tour = rng.permutation(n)
     sol = np.zeros(d, dtype=np.uint8)
     for a in range(n):
         sol[eidx[tour[a], tour[(a + 1) % n]]] = 1

@@ -176,6 +176,15 @@ int cave_dense_gram(const float* A, int64_t B, int64_t m_max, int64_t d, const c
                     float* G_out, int32_t* n_dense_out, void* pack, size_t pack_bytes,
                     void* scratch, size_t scratch_bytes, void* stream);
 
+/* Auxiliary, evaluation only (not on the hot path): exact symmetric TSP by Held-Karp dynamic programming for
+ * n_nodes <= 20, one CTA per instance.  Decision regret (BASELINE.json configs[1]; the reference's code_sample.py
+ * evaluates with pyepo.metric.regret, which calls Gurobi through src/model/tsp.py) needs optimal tours under predicted
+ * and true costs.  cost: [N, n(n-1)/2] float32 edge costs, edges (i<j) in lexicographic order; tour: [N, n_nodes]
+ * node sequence starting at 0; obj: [N] float64 tour length.  scratch: cave_tsp_scratch_bytes(). */
+int cave_tsp_scratch_bytes(int64_t N, int32_t n_nodes, size_t* out);
+int cave_tsp_solve(const float* cost, int64_t N, int32_t n_nodes, int32_t* tour, double* obj, void* scratch, size_t scratch_bytes,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

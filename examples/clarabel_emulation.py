@@ -34,7 +34,9 @@ def project_ipm_truncated(A: torch.Tensor, c: torch.Tensor, iters: int = 3) -> t
     for _ in range(iters):
         r_d = (G @ lam[:, :, None]).squeeze(2) - b - z        # dual residual
         mu = (lam * z).sum(1, keepdim=True) / m
-        H = G + torch.diag_embed(z / lam)
+        if float(mu.max()) < 1e-13:                          # converged to machine precision (only reached with many iterations)
+            break
+        H = G + torch.diag_embed(z / lam + 1e-12)
         # predictor (affine scaling)
         rhs = -r_d - z
         dl_a = torch.linalg.solve(H, rhs[:, :, None]).squeeze(2)

@@ -178,6 +178,9 @@ def test_module_accepts_sparse_constraints_and_packs():
     A = synth.densify(insts, device=dev)
     pred = synth.predictions(insts, 4, "near")
     mod = innerConeAlignedCosine(_Model(EPO.MINIMIZE), solver="cuda", seed=0)
+    # recycled allocator memory must not be mistaken for a cached solver setup: leave valid-looking garbage behind
+    junk = torch.ones(64 << 20, dtype=torch.int32, device=dev)
+    del junk
     p0 = torch.tensor(pred, device=dev, requires_grad=True)
     l0 = mod(p0, A); l0.backward()
     sc = SparseConstraints.from_instances(insts)

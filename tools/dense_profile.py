@@ -6,7 +6,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from cave_b200 import _lib, cave_forward_backward
 
-NAMES = ["setup", "kkt", "freeset", "gather", "chol", "trisolve", "ls_gram", "ls_true", "truegrad", "epilogue", "switch", "n_fact", "n_iter"]
+NAMES = ["setup", "kkt", "freeset", "gather", "chol", "trisolve", "ls_gram", "ls_true", "truegrad", "epilogue", "switch", "n_fact", "n_iter",
+         "chol:update", "chol:diag", "chol:trsm"]
 dev = torch.device("cuda:0")
 d, m, B = (int(x) for x in sys.argv[1:4])
 g = torch.Generator(device=dev).manual_seed(d * 7 + m)
@@ -23,7 +24,9 @@ ints = blk[:64].view(torch.int32).tolist(); prof = blk[64:192].view(torch.int64)
 tot = sum(prof[:11])
 print(f"d={d} m={m} B={B}: {B / dt:.1f} inst/s ({dt * 1e3:.1f} ms), dense instances {ints[0]}, iters mean {out['iters'].float().mean():.1f}")
 for n, v in zip(NAMES, prof):
-    if n.startswith("n_"):
+    if n.startswith("chol:"):
+        print(f"  {n:12s} {v / max(ints[0], 1) / 1e3:10.1f} kclk per instance")
+    elif n.startswith("n_"):
         print(f"  {n:10s} {v / max(ints[0], 1):8.2f} per instance")
     else:
         print(f"  {n:10s} {v / max(ints[0], 1) / 1e3:10.1f} kclk per instance  {100.0 * v / max(tot, 1):5.1f} %")

@@ -363,7 +363,8 @@ def run_ours(args):
 
     # ---- per-kernel timings for the roofline (same stream, CUDA events, same inputs)
     pack = pack_constraints(A)
-    ms_scan = timed(lambda: pack_constraints(A), max(3, args.steps // 2))
+    ms_scan = timed(lambda: pack_constraints(A, cache_setup=False), max(3, args.steps // 2))     # scan + plan + order: what a cold step runs
+    ms_pack = timed(lambda: pack_constraints(A), max(3, args.steps // 2))                         # + the setup kernel (reusable packs)
     warm = lambda: cave_forward_backward(pred, A, -1.0, mode, ratio, "mean", precision=args.precision, pack=pack)  # noqa: E731
     warm()
     ms_solve = timed(warm, max(3, args.steps // 2))
@@ -377,9 +378,11 @@ def run_ours(args):
         {"name": "scan_kernel", "ms": ms_scan, "bytes": scan_bytes, "gbs": scan_bytes / ms_scan / 1e6,
          "frac_of_hbm_peak": scan_bytes / ms_scan / 1e6 / hbm_peak},
         {"name": "solve_kernel+finalize", "ms": ms_solve, "bytes": solve_bytes, "gbs": solve_bytes / ms_solve / 1e6,
-         "note": "shared-memory / latency bound; reads only the general rows of A"},
+         "note": "shared-memory / latency bound; WARM pack (cached solver setup: copy-in); a cold step runs the in-solver setup "
+                 "instead (step - scan)"},
+        {"name": "setup_kernel (reusable packs only, not in the cold step)", "ms": ms_pack - ms_scan},
     ]
-    dom = max(kernels, key=lambda k: k["ms"])
+    dom = max(kernels[:2], key=lambda k: k["ms"])
     # step-level roofline: algorithmic bytes of the whole path over the whole step, against HBM
     achieved = alg_bytes / ms_step / 1e6
     tr = _traffic_from_profile(args.workload, B)
@@ -387,6 +390,11 @@ def run_ours(args):
                 "traffic": tr["bytes_per_step"] if tr else None, "traffic_source": tr, "peak_source": peak_src,
                 "dominant_kernel": dom["name"], "algorithmic_bytes_per_step": alg_bytes,
                 "note": "achieved = sum_i (4 m_i d + 8 d + 4) bytes / step time; per-kernel split in `kernels`"}
+    # the same roofline figure for the device-resident packed dataset (warm pack: no pass over A, cached solver setup);
+    # a packed resident layout may exceed 100 % of the dense-input figure; its own traffic is ~1 % of it
+    roofline["resident_pack"] = {"ms_per_step": ms_solve, "inst_per_s": B * world / (ms_solve * 1e-3),
+                                 "frac_of_dense_input_roofline": alg_bytes / ms_solve / 1e6 / hbm_peak,
+                                 "note": "warm / dataset pack (what every epoch after the first runs): latency bound, not HBM bound"}
 
     # ---- end to end through the module call with host tensors
     e2e = None

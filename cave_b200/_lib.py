@@ -18,7 +18,7 @@ ST_CONVERGED, ST_ITER_CAP, ST_STALLED, ST_NOSPACE, ST_SKIPPED, ST_BADINPUT, ST_P
 EXPORTS = ("cave_abi_version", "cave_last_error", "cave_get_limits", "cave_pack_bytes",
            "cave_scratch_bytes", "cave_pack", "cave_forward_backward", "cave_plan_offset", "cave_plan_choice",
            "cave_dense_gram", "cave_launch_count", "cave_dense_ctrl_offset", "cave_pack_sparse",
-           "cave_tsp_scratch_bytes", "cave_tsp_solve")
+           "cave_tsp_scratch_bytes", "cave_tsp_solve", "cave_pack_ex")
 
 
 class SolverOpts(ctypes.Structure):
@@ -58,6 +58,7 @@ def load() -> ctypes.CDLL:
     lib.cave_pack_bytes.argtypes = [I64, I64, I64, SZP]
     lib.cave_scratch_bytes.argtypes = [I64, I64, I64, I32, ctypes.POINTER(SolverOpts), SZP]
     lib.cave_pack.argtypes = [P, P, I64, I64, I64, P, ctypes.c_size_t, P]
+    lib.cave_pack_ex.argtypes = [P, P, I64, I64, I64, I32, P, ctypes.c_size_t, P]
     lib.cave_forward_backward.argtypes = [P, P, P, I64, I64, I64, F, I32, F, I32, I32, I32,
                                           ctypes.POINTER(SolverOpts), P, P, P, P, P, P, P,
                                           P, ctypes.c_size_t, P, ctypes.c_size_t, P]
@@ -71,7 +72,7 @@ def load() -> ctypes.CDLL:
     lib.cave_plan_choice.argtypes = [ctypes.POINTER(ctypes.c_uint64), I64, I32, I32, IP, IP, IP]
     for name in ("cave_get_limits", "cave_pack_bytes", "cave_scratch_bytes", "cave_pack", "cave_forward_backward",
                  "cave_plan_offset", "cave_plan_choice", "cave_dense_gram", "cave_dense_ctrl_offset", "cave_pack_sparse",
-           "cave_tsp_scratch_bytes", "cave_tsp_solve"):
+           "cave_tsp_scratch_bytes", "cave_tsp_solve", "cave_pack_ex"):
         getattr(lib, name).restype = I32
     _lib = lib
     return lib

@@ -253,6 +253,11 @@ int cave_pack(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, i
     return pack_impl(A, m_rows, B, m_max, d, pack, pack_bytes, stream, true);
 }
 
+int cave_pack_ex(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, int64_t d, int32_t flags, void* pack,
+                 size_t pack_bytes, void* stream) {
+    return pack_impl(A, m_rows, B, m_max, d, pack, pack_bytes, stream, (flags & 1) != 0);
+}
+
 int cave_pack_sparse(const int64_t* inst_off, const int64_t* row_ptr, const int32_t* col, const float* val, int64_t B,
                      int64_t m_max, int64_t d, int32_t flags, void* pack, size_t pack_bytes, void* stream) {
     if (!inst_off || !row_ptr || !col || !val) return fail(CAVE_EINVAL, "inst_off, row_ptr, col and val must not be null");

@@ -94,7 +94,8 @@ class CavePack:
                 "max_hot_bytes_f64": words[3], "max_hot_bytes_f32": words[4]}
 
 
-def pack_constraints(tight_ctrs: torch.Tensor, m_rows: torch.Tensor | None = None, keep_dense: bool = True) -> CavePack:
+def pack_constraints(tight_ctrs: torch.Tensor, m_rows: torch.Tensor | None = None, keep_dense: bool = True,
+                     cache_setup: bool = True) -> CavePack:
     lib = _lib.load()
     if not tight_ctrs.is_cuda:
         raise ValueError("pack_constraints expects a CUDA tensor")
@@ -107,7 +108,8 @@ def pack_constraints(tight_ctrs: torch.Tensor, m_rows: torch.Tensor | None = Non
     buf = torch.empty(nbytes.value, dtype=torch.uint8, device=A.device)
     with torch.cuda.device(A.device):
         stream = torch.cuda.current_stream(A.device).cuda_stream
-        _lib.check(lib.cave_pack(_ptr(A), _ptr(m_rows), B, m, d, _ptr(buf), nbytes.value, ctypes.c_void_p(stream)))
+        _lib.check(lib.cave_pack_ex(_ptr(A), _ptr(m_rows), B, m, d, 1 if cache_setup else 0, _ptr(buf), nbytes.value,
+                                    ctypes.c_void_p(stream)))
     return CavePack(buf, (B, m, d), A.data_ptr(), A if keep_dense else None, int(tight_ctrs._version))
 
 

@@ -134,6 +134,11 @@ int cave_scratch_bytes(int64_t B, int64_t m_max, int64_t d, int compute_dtype,
 int cave_pack(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, int64_t d,
               void* pack, size_t pack_bytes, void* stream);
 
+/* cave_pack with flags: bit 0 = also emit the cached per-instance solver setup (cave_pack() sets it; a pack that is used
+ * once does without: the setup kernel costs about what one solve saves). */
+int cave_pack_ex(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, int64_t d, int32_t flags,
+                 void* pack, size_t pack_bytes, void* stream);
+
 /* Sparse ingestion: the same pack built from the non-zeros of the binding-constraint rows instead of the dense padded
  * tensor (every shipped model is 0.7 % dense at TSP-50: 90 KB instead of 6.5 MB per instance cross PCIe and HBM).
  * Replaces DataLoader + collate_fn's dense zero padding (src/dataset.py:114-144) for callers that keep `dataset.ctrs`

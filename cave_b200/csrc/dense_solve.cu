@@ -26,6 +26,7 @@ constexpr int kKS = 16;             // k-slab of the update
 
 struct DenseSmem {
     double *lam, *lamt, *g, *gt, *dir, *bb;
+    double *lamp;                   // the trial point, 32 x 4 transposed inside every 128-block: conflict-free reads in the matvec
     int *fl, *flp;
     int *arow, *sup;                // row of A behind every variable; support list of the point being evaluated
     float *As, *Bs, *D, *Dt, *invd;
@@ -42,7 +43,7 @@ struct DenseSmem {
 
 __host__ __device__ inline size_t dense_solve_smem(int64_t m_pad) {
     size_t o = 0;
-    o += 6 * (size_t)m_pad * 8;                 // lam lamt g gt dir bb
+    o += 7 * (size_t)m_pad * 8;                 // lam lamt g gt dir bb lamp
     o += 4 * (size_t)m_pad * 4;                 // free lists, arow, sup
     o += (size_t)m_pad * 4;                     // xs
     o += (size_t)kKS * kRC * 4 + (size_t)kKS * kNB * 4;     // As, Bs
@@ -361,8 +362,8 @@ __device__ void chol_solve_blocked(const float* __restrict__ W, int ldw, int nf,
 
 // gt = G lamt - bb over all m rows (float64 accumulation); returns lamt^T gt and bb^T lamt.  The rows come from L2 / HBM with
 // a latency of microseconds under load, so every warp keeps two rows = up to sixteen 16-byte loads per lane in flight.
-__device__ void gram_matvec(const float* __restrict__ G, int ldg, int m, const double* lamt, const double* bb, double* gt,
-                            Ctx& cx, double& lg, double& lb) {
+__device__ void gram_matvec(const float* __restrict__ G, int ldg, int m, const double* lamt, const double* lamp, const double* bb,
+                            double* gt, Ctx& cx, double& lg, double& lb) {
     double a_lg = 0.0, a_lb = 0.0;
     for (int v0 = 2 * cx.warp; v0 < m; v0 += 2 * cx.nwarp) {
         const bool two = v0 + 1 < m;
@@ -381,7 +382,9 @@ __device__ void gram_matvec(const float* __restrict__ G, int ldg, int m, const d
             for (int u = 0; u < 8; ++u) {
                 const int j = j0 + u * 128;
                 if (j < m) {
-                    const double l0 = lamt[j], l1 = lamt[j + 1], l2 = lamt[j + 2], l3 = lamt[j + 3];
+                    // lamp holds column (base + 4 lane + c) at base + 32 c + lane: consecutive lanes, consecutive words
+                    const int pb = (j & ~127) + cx.lane;
+                    const double l0 = lamp[pb], l1 = lamp[pb + 32], l2 = lamp[pb + 64], l3 = lamp[pb + 96];
                     s0 += (double)g0[u].x * l0 + (double)g0[u].y * l1 + (double)g0[u].z * l2 + (double)g0[u].w * l3;
                     s1 += (double)g1[u].x * l0 + (double)g1[u].y * l1 + (double)g1[u].z * l2 + (double)g1[u].w * l3;
                 }
@@ -503,6 +506,7 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
         S.lam = (double*)o; o += (size_t)mp * 8; S.lamt = (double*)o; o += (size_t)mp * 8;
         S.g = (double*)o; o += (size_t)mp * 8; S.gt = (double*)o; o += (size_t)mp * 8;
         S.dir = (double*)o; o += (size_t)mp * 8; S.bb = (double*)o; o += (size_t)mp * 8;
+        S.lamp = (double*)o; o += (size_t)mp * 8;
         S.fl = (int*)o; o += (size_t)mp * 4; S.flp = (int*)o; o += (size_t)mp * 4;
         S.arow = (int*)o; o += (size_t)mp * 4; S.sup = (int*)o; o += (size_t)mp * 4;
         S.xs = (float*)o; o += (size_t)mp * 4;
@@ -667,11 +671,12 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
                         double t = 0.0;
                         if (v < m) { t = lam[v] - alpha * S.dir[v]; if (t < 0.0) t = 0.0; dec += g[v] * (lam[v] - t); }
                         lamt[v] = t;
+                        S.lamp[(v & ~127) + ((v & 3) << 5) + ((v >> 2) & 31)] = t;
                     }
                     dec = cx.block_sum(dec);
                     if (phase == 1) {
                         double lg, lb;
-                        gram_matvec(G, mp, m, lamt, S.bb, gt, cx, lg, lb);
+                        gram_matvec(G, mp, m, lamt, S.lamp, S.bb, gt, cx, lg, lb);
                         ft = 0.5 * lg - 0.5 * lb;
                         DPROF(DP_LS_GRAM);
                     } else {

@@ -227,3 +227,60 @@ def test_held_karp_is_exact_against_brute_force_and_bounds():
                         t, improved = t2, True
         assert obj[i] <= length(t) + 1e-6
         assert obj[i] <= length(list(range(n))) + 1e-6
+
+
+def test_no_write_outside_the_callers_buffers():
+    """compute-sanitizer is closed on this pool, so the out-of-bounds check is our own: pack, scratch and every output of the
+    C-ABI call sit between poisoned guard bands that must come back untouched — structured (Newton), Lawson-Hanson, the dense
+    tensor-core path (two rounds) and a dataset-indexed call."""
+    import ctypes
+    from cave_b200 import _lib, synth
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    G = 1 << 16                                   # guard band, bytes
+
+    def guarded(nbytes):
+        buf = torch.full((nbytes + 2 * G + 512,), 0xA5, dtype=torch.uint8, device=dev)
+        off = (-buf.data_ptr() - G) % 256 + G      # 256-byte aligned payload
+        return buf, off
+
+    def check(buf, off, nbytes, what):
+        assert bool((buf[:off] == 0xA5).all()) and bool((buf[off + nbytes:] == 0xA5).all()), f"guard band of {what} overwritten"
+
+    def run(A, pred, mode, opts, index=None, n_packed=0):
+        B, m, d = A.shape
+        Bq = pred.shape[0]
+        nb = ctypes.c_size_t()
+        _lib.check(lib.cave_pack_bytes(B, m, d, ctypes.byref(nb))); pbytes = nb.value
+        _lib.check(lib.cave_scratch_bytes(Bq, m, d, _lib.F64, ctypes.byref(opts), ctypes.byref(nb))); sbytes = nb.value
+        bufs = {"pack": guarded(pbytes) + (pbytes,), "scratch": guarded(sbytes) + (sbytes,)}
+        for name, n in (("loss", 4), ("loss_i", 4 * Bq), ("grad", 4 * Bq * d), ("proj", 4 * Bq * d), ("rnorm", 4 * Bq), ("status", 4 * Bq), ("iters", 4 * Bq)):
+            bufs[name] = guarded(n) + (n,)
+        ptr = lambda k: ctypes.c_void_p(bufs[k][0].data_ptr() + bufs[k][1])  # noqa: E731
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        if index is not None:
+            _lib.check(lib.cave_pack(ctypes.c_void_p(A.data_ptr()), None, B, m, d, ptr("pack"), pbytes, stream))
+        _lib.check(lib.cave_forward_backward(ctypes.c_void_p(A.data_ptr()), None, ctypes.c_void_p(pred.data_ptr()), Bq, m, d, -1.0, mode, 0.2, 0,
+                                             _lib.F32, _lib.F64, ctypes.byref(opts), ptr("loss"), ptr("loss_i"), ptr("grad"), ptr("proj"),
+                                             ptr("rnorm"), ptr("status"), ptr("iters"), ptr("pack"), pbytes, ptr("scratch"), sbytes, stream))
+        torch.cuda.synchronize()
+        for k, (buf, off, n) in bufs.items():
+            check(buf, off, n, k)
+        st = bufs["status"][0][bufs["status"][1]:bufs["status"][1] + 4 * Bq].view(torch.int32)
+        return st.cpu().numpy()
+
+    insts = synth.make_batch("tsp20", 12, seed=2)
+    A = synth.densify(insts, device=dev)
+    pred = torch.tensor(synth.predictions(insts, 2, "near"), device=dev)
+    st = run(A, pred, 1, _lib.SolverOpts(0, 0, 0.0, 0, 0, 0, 0, None, 0, 0))
+    assert ((st & 0xff) == 0).all()
+    idx = torch.tensor([5, 0, 11, 3], dtype=torch.int32, device=dev)
+    st = run(A, pred[idx.long()].contiguous(), 1, _lib.SolverOpts(0, 0, 0.0, 0, 0, 1, 0, idx.data_ptr(), 12, 0), index=idx)
+    assert ((st & 0xff) == 0).all()
+    g = torch.Generator(device=dev).manual_seed(1)
+    A = torch.randn((5, 40, 24), generator=g, device=dev); c = torch.randn((5, 24), generator=g, device=dev)
+    st = run(A, c, 0, _lib.SolverOpts(0, 0, 0.0, 0, 0, 0, 0, None, 0, 0))
+    assert ((st & _lib.ST_PATH_LH) != 0).all()
+    A = torch.randn((5, 200, 260), generator=g, device=dev); A[3, 190:] = 0; c = torch.randn((5, 260), generator=g, device=dev)
+    st = run(A, c, 0, _lib.SolverOpts(0, 0, 0.0, 0, 0, 0, 1, None, 0, 2))            # dense path, slots = 2 -> three rounds
+    assert ((st & _lib.ST_PATH_GRAM) != 0).all() and ((st & 0xff) == 0).all()

@@ -288,12 +288,12 @@ def run_ours(args):
     def sweep_point(d, m, batch, steps, want_cpu):
         g = torch.Generator(device=dev).manual_seed(1000 + rank)
         A = torch.randn((batch, m, d), generator=g, device=dev)
-        c = torch.randn((batch, d), generator=g, device=dev)
-        step = lambda: cave_forward_backward(c, A, 1.0, 0, 0.0, "mean", precision=args.precision)  # noqa: E731
+        c = -torch.randn((batch, d), generator=g, device=dev)       # pred_cost; the signed cost is -pred (MINIMIZE, src/cave.py:62-64)
+        step = lambda: cave_forward_backward(c, A, -1.0, 0, 0.0, "mean", precision=args.precision)  # noqa: E731
         for _ in range(2):
             step()
         ms = timed(step, steps)
-        st = cave_forward_backward(c, A, 1.0, 0, 0.0, "none", precision=args.precision, want_status=True)
+        st = cave_forward_backward(c, A, -1.0, 0, 0.0, "none", precision=args.precision, want_status=True)
         status = st["status"].cpu().numpy()
         flops = float(batch) * (float(m) * m * d + 4.0 * m * d)                # SURVEY 8d "Algorithmic flops"
         info = {"d": d, "m": m, "batch_per_gpu": batch, "inst_per_s": batch * world / (ms * 1e-3), "ms_per_step": ms,
@@ -316,7 +316,7 @@ def run_ours(args):
                                    "note": "TF32 split + Gram + D2D copy of G, pack pass subtracted; executed flops = 3 x m^2 d"}
         if want_cpu:
             n = max(4, min(2 * cores, 16))
-            work = [(-c[b].cpu().numpy(), A[b].cpu().numpy(), 0, 0.0) for b in range(n)]
+            work = [(c[b].cpu().numpy(), A[b].cpu().numpy(), 0, 0.0) for b in range(n)]
             rate, res = cpu_rate(work)
             info["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{n} instances of this batch"}
             info["parity_sample"] = parity(work, res, st["loss_i"], st["grad"])

@@ -93,13 +93,20 @@ bool resolve_caps(const cave_solver_opts* o, int64_t m_max, int64_t d, int64_t* 
     return explicit_caps;
 }
 
-struct ScratchPlan { int64_t cr, cz, n_slots, n_large; size_t large_bytes; };
+struct ScratchPlan { int64_t cr, cz, n_slots, n_large; size_t large_bytes, small_bytes; };
 ScratchPlan plan_scratch(const cave_solver_opts* o, int64_t B, int64_t m_max, int64_t d);
 
 ScratchPlan plan_scratch(const cave_solver_opts* o, int64_t B, int64_t m_max, int64_t d) {
     ScratchPlan P;
     const bool explicit_caps = resolve_caps(o, m_max, d, &P.cr, &P.cz);
-    const size_t small = cave::solver_slot_bytes(d, P.cr, P.cz, 8);
+    size_t small = cave::solver_slot_bytes(d, P.cr, P.cz, 8);
+    if (!explicit_caps) {
+        // Lawson-Hanson instances with many rows but a passive set of at most 192 columns (e.g. d = 190, m = 1024) stay in
+        // the small slot as well
+        const size_t lh_many_rows = cave::align_up(cave::lh_slot_bytes(d, m_max, 8, 192) + 64 * 16 + 1024, 256);
+        if (lh_many_rows > small) small = lh_many_rows;
+    }
+    P.small_bytes = small;
     P.n_slots = solver_slots(B, small);
     P.n_large = 0; P.large_bytes = 0;
     if (!explicit_caps) {
@@ -171,7 +178,7 @@ int cave_dense_ctrl_offset(int64_t B, int64_t m_max, int64_t d, const cave_solve
     if (!out) return fail(CAVE_EINVAL, "out is null");
     if (int e = check_shape(B, m_max, d)) return e;
     const ScratchPlan SPn = plan_scratch(opts, B, m_max, d);
-    const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, SPn.cr, SPn.cz, 8, SPn.n_slots, SPn.n_large, SPn.large_bytes);
+    const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, SPn.cr, SPn.cz, 8, SPn.n_slots, SPn.n_large, SPn.large_bytes, SPn.small_bytes);
     *out = cave::make_dense_layout(B, m_max, d, dense_slots(opts, B, m_max, d), SL.total).ctrl;
     return CAVE_OK;
 }
@@ -194,7 +201,7 @@ int cave_scratch_bytes(int64_t B, int64_t m_max, int64_t d, int compute_dtype, c
     if (int e = check_shape(B, m_max, d)) return e;
     if (compute_dtype != CAVE_F32 && compute_dtype != CAVE_F64) return fail(CAVE_EINVAL, "bad compute_dtype %d", compute_dtype);
     const ScratchPlan SPn = plan_scratch(opts, B, m_max, d);
-    size_t total = cave::make_scratch_layout(B, d, SPn.cr, SPn.cz, 8, SPn.n_slots, SPn.n_large, SPn.large_bytes).total;
+    size_t total = cave::make_scratch_layout(B, d, SPn.cr, SPn.cz, 8, SPn.n_slots, SPn.n_large, SPn.large_bytes, SPn.small_bytes).total;
     // mode and A are not known here: sized for the case that the call takes the dense path
     static const float kSomeA = 0.f;
     if (dense_enabled(opts, &kSomeA, m_max, d, CAVE_MODE_EXACT))
@@ -292,7 +299,7 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     const ScratchPlan SPn = plan_scratch(opts, B, m_max, d);
     const size_t T = 8;   // state vectors are double in both modes; sized for the f64 factor
     const int64_t n_slots = SPn.n_slots;
-    const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, SPn.cr, SPn.cz, T, n_slots, SPn.n_large, SPn.large_bytes);
+    const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, SPn.cr, SPn.cz, T, n_slots, SPn.n_large, SPn.large_bytes, SPn.small_bytes);
     const bool dense = dense_enabled(opts, A, m_max, d, mode);
     cave::DenseLayout DL;
     memset(&DL, 0, sizeof(DL));
@@ -433,7 +440,7 @@ int cave_dense_gram(const float* A, int64_t B, int64_t m_max, int64_t d, const c
     const cave::PackLayout PL = cave::make_pack_layout(B, m_max, d);
     if (pack_bytes < PL.total) return fail(CAVE_ENOSPC, "pack buffer has %zu bytes, %zu needed", pack_bytes, PL.total);
     const ScratchPlan SPn = plan_scratch(&o, B, m_max, d);
-    const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, SPn.cr, SPn.cz, 8, SPn.n_slots, SPn.n_large, SPn.large_bytes);
+    const cave::ScratchLayout SL = cave::make_scratch_layout(B, d, SPn.cr, SPn.cz, 8, SPn.n_slots, SPn.n_large, SPn.large_bytes, SPn.small_bytes);
     const cave::DenseLayout DL = cave::make_dense_layout(B, m_max, d, dense_slots(&o, B, m_max, d), SL.total);
     if (scratch_bytes < DL.total) return fail(CAVE_ENOSPC, "scratch buffer has %zu bytes, %zu needed", scratch_bytes, DL.total);
     char* pb = (char*)pack;

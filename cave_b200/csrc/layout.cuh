@@ -157,20 +157,31 @@ struct ScratchLayout {
     int64_t n_slots, n_large;
 };
 
+// Newton path (upper bound over every Arena::get in nw_setup / newton_solve) for `rows` general rows with `nnz` non-zeros
+CAVE_HD size_t newton_slot_bytes(int64_t d, int64_t rows, int64_t nnz, size_t T) {
+    const size_t r = (size_t)rows + 2, dd = (size_t)d + 2;
+    return 3 * dd * T + 4 * dd + 4 * dd + 4 * dd + 64 + r * (6 * T + 4 + 4 + 1 + 4 + 1 + 4 + 4 + 8 + 4)
+           + (size_t)(nnz + 2) * 12 + (r * (r + 1) / 2 + (r + 2) * (r + 3) / 2 + 8) * T;
+}
+// Lawson-Hanson path: `rows` general rows, passive set of at most kcap = min(rows, d) columns
+CAVE_HD size_t lh_slot_bytes(int64_t d, int64_t rows, size_t T, int64_t kcap = -1) {
+    const size_t r = (size_t)rows + 2, dd = (size_t)d + 2;
+    int64_t kk = rows < d ? rows : d;
+    if (kcap >= 0 && kk > kcap) kk = kcap;
+    const size_t k = (size_t)kk + 2;
+    return 3 * dd * T + dd * T + k * (5 * T + 8) + r * 5 + 2 * k * k * T;
+}
 CAVE_HD size_t solver_slot_bytes(int64_t d, int64_t cap_rows, int64_t cap_nnz, size_t T) {
-    const size_t r = (size_t)cap_rows + 2, dd = (size_t)d + 2;
-    // Newton path (upper bound over every Arena::get in nw_setup / newton_solve)
-    size_t nw = 3 * dd * T + 4 * dd + 4 * dd + 4 * dd + 64 + r * (6 * T + 4 + 4 + 1 + 4 + 1 + 4 + 4 + 8 + 4)
-              + (size_t)(cap_nnz + 2) * 12 + (r * (r + 1) / 2 + (r + 2) * (r + 3) / 2 + 8) * T;
-    // Lawson-Hanson path
-    const size_t k = (cap_rows < d ? (size_t)cap_rows : (size_t)d) + 2;
-    size_t lh = 3 * dd * T + dd * T + k * (5 * T + 8) + r * 5 + 2 * k * k * T;
-    size_t m = nw > lh ? nw : lh;
-    return align_up(m + 64 * 16 + 1024, 256);
+    const size_t nw = newton_slot_bytes(d, cap_rows, cap_nnz, T), lh = lh_slot_bytes(d, cap_rows, T);
+    return align_up((nw > lh ? nw : lh) + 64 * 16 + 1024, 256);
+}
+// what ONE instance needs from its slot, by the path it will take (no singleton row: Lawson-Hanson, else Newton)
+CAVE_HD size_t instance_slot_bytes(int64_t d, int64_t ngen, int64_t gen_nnz, bool lh_path, size_t T) {
+    return align_up((lh_path ? lh_slot_bytes(d, ngen, T) : newton_slot_bytes(d, ngen, gen_nnz, T)) + 64 * 16 + 1024, 256);
 }
 
 CAVE_HD ScratchLayout make_scratch_layout(int64_t B, int64_t d, int64_t cap_rows, int64_t cap_nnz, size_t T,
-                                          int64_t n_slots, int64_t n_large = 0, size_t large_bytes = 0) {
+                                          int64_t n_slots, int64_t n_large = 0, size_t large_bytes = 0, size_t small_bytes = 0) {
     ScratchLayout L;
     size_t o = 0;
     L.counter = o; o = align_up(o + 256, 256);          // int[0] work counter, int[8 .. 8 + n_large) slot locks
@@ -178,7 +189,7 @@ CAVE_HD ScratchLayout make_scratch_layout(int64_t B, int64_t d, int64_t cap_rows
     L.rnorm64 = o; o = align_up(o + (size_t)B * 8, 256);
     L.status = o;  o = align_up(o + (size_t)B * 4, 256);
     L.iters = o;   o = align_up(o + (size_t)B * 4, 256);
-    L.slot_bytes = solver_slot_bytes(d, cap_rows, cap_nnz, T);
+    L.slot_bytes = small_bytes ? small_bytes : solver_slot_bytes(d, cap_rows, cap_nnz, T);
     L.n_slots = n_slots;
     L.slots = o;   o += L.slot_bytes * (size_t)n_slots;
     L.n_large = n_large; L.large_bytes = large_bytes;

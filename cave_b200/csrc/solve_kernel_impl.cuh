@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(CAVE_LB_T, CAVE_LB_C) solve_kernel(SolveParams
         // an instance whose working set cannot fit this CTA's slot borrows one of the worst-case slots under a lock
         char* islot = slot; size_t islot_bytes = p.slot_bytes;
         int held = -1;
-        if (p.n_large > 0 && in.ngen > 0 && solver_slot_bytes(p.d, in.ngen, in.gen_nnz, 8) > p.slot_bytes) {
+        if (p.n_large > 0 && in.ngen > 0 && instance_slot_bytes(p.d, in.ngen, in.gen_nnz, in.nsingc == 0, 8) > p.slot_bytes) {
             if (cx.tid == 0) {
                 int got = -1;
                 unsigned ns = 64;

@@ -110,7 +110,7 @@ struct SolveConfig { int threads, ctas_per_sm, smem_bytes; };
 constexpr int kNumSolveConfigs = 4;
 CAVE_HD SolveConfig solve_config(int i) {
     // 4 x 128 x 128 registers fills the register file; shared memory per CTA leaves room for the static part
-    const SolveConfig t[kNumSolveConfigs] = {{64, 8, 28160}, {128, 4, 56320}, {160, 3, 75776}, {256, 2, 112640}};
+    const SolveConfig t[kNumSolveConfigs] = {{64, 8, 27520}, {128, 4, 56320}, {160, 3, 75776}, {256, 2, 112640}};
     return t[i];
 }
 CAVE_HD size_t a16(size_t v) { return (v + 15) & ~(size_t)15; }

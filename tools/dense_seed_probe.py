@@ -1,0 +1,19 @@
+"""Which instances of a seeded dense batch leave the Gram path (status / iterations), for robustness work."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from cave_b200 import cave_forward_backward
+dev = torch.device("cuda:0")
+d, m, B = (int(x) for x in sys.argv[1:4])
+for seed in [int(s) for s in sys.argv[4:]] or [1000, 1001]:
+    g = torch.Generator(device=dev).manual_seed(seed)
+    A = torch.randn((B, m, d), generator=g, device=dev)
+    c = -torch.randn((B, d), generator=g, device=dev)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    out = cave_forward_backward(c, A, -1.0, 0, 0.0, "none", want_status=True)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    st = out["status"].cpu().numpy(); it = out["iters"].cpu().numpy()
+    vals, cnts = np.unique(st, return_counts=True)
+    print(f"seed {seed}: {B / dt:.1f} inst/s; status counts {dict(zip([hex(v) for v in vals], cnts.tolist()))}; iters mean {it.mean():.1f} max {it.max()}", flush=True)
+    bad = np.flatnonzero((st & 0x200) == 0)
+    print("   instances off the Gram path:", bad[:20].tolist(), "iters", it[bad][:20].tolist())

@@ -350,7 +350,7 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
         dp.A = A; dp.pred = pred; dp.B = (int)B; dp.m_max = (int)m_max; dp.d = (int)d;
         dp.inst_index = sp.inst_index; dp.n_packed = Bpack; dp.nvalid = sp.nvalid; dp.ngen = sp.ngen; dp.nsingc = sp.nsingc; dp.gen = sp.gen;
         dp.ctype = sp.ctype; dp.avg = sp.avg; dp.dpad = PL.dpad;
-        dp.ws = sb; dp.L = DL; dp.force = (opts && opts->dense_mode > 0) ? 1 : 0;
+        dp.ws = sb; dp.L = DL; dp.force = (opts && opts->dense_mode > 0) ? 1 : 0; dp.no_handback = env_int("CAVE_DENSE_NO_HANDBACK", 0); dp.trace_b = env_int("CAVE_DENSE_TRACE", -1);
         dp.grad = grad; dp.proj = proj; dp.loss64 = sp.loss64; dp.rnorm64 = sp.rnorm64; dp.status = sp.status; dp.iters = sp.iters;
         dp.mode = mode; dp.inner_ratio = inner_ratio; dp.sign = sign; dp.gscale = sp.gscale;
         dp.max_iter = 0; dp.max_ls = sp.max_ls; dp.tol = sp.tol; dp.io_f32 = io_dtype == CAVE_F32; dp.nk = (int)(DL.d_pad / 32);
@@ -452,7 +452,7 @@ int cave_dense_gram(const float* A, int64_t B, int64_t m_max, int64_t d, const c
     dp.A = A; dp.pred = &kZero; dp.B = (int)B; dp.m_max = (int)m_max; dp.d = (int)d; dp.n_packed = B;
     dp.nvalid = (const int*)(pb + PL.nvalid); dp.ngen = (const int*)(pb + PL.ngen); dp.nsingc = (const int*)(pb + PL.nsingc);
     dp.gen = (const int4*)(pb + PL.gen); dp.ctype = (const unsigned char*)(pb + PL.ctype); dp.avg = (const float*)(pb + PL.avg);
-    dp.dpad = PL.dpad; dp.ws = sb; dp.L = DL; dp.force = 1; dp.sign = 0.0; dp.io_f32 = 1; dp.nk = (int)(DL.d_pad / 32);
+    dp.dpad = PL.dpad; dp.ws = sb; dp.L = DL; dp.force = 1; dp.trace_b = -1; dp.sign = 0.0; dp.io_f32 = 1; dp.nk = (int)(DL.d_pad / 32);
     // prep reads pred[b * d + k] for the right-hand side b = A c: point it at A's first rows (any finite data will do)
     dp.pred = A;
     cudaError_t ce = cave::launch_dense_list(dp, st);

@@ -85,6 +85,9 @@ struct DenseParams {
     char* ws;                   // scratch base
     DenseLayout L;
     int round;                  // this launch handles dense instances [round * n_slots, (round + 1) * n_slots)
+    int trace_b;                // diagnostics (CAVE_DENSE_TRACE=<batch index>): per-iteration printf of that instance, -1 off
+    int no_handback;            // diagnostics (CAVE_DENSE_NO_HANDBACK=1): keep the result of an instance that would be handed back,
+                                // status |= reason << 16 (1 phase-1 cap, 2 phase-1 stall, 3 phase-2 cap, 4 phase-2 stall) | phase << 12
     int force;                  // 1: every instance without singleton rows and >= kDenseMinRows rows qualifies
     // outputs
     void* grad; void* proj;

@@ -14,6 +14,7 @@
 // is handed back: its flag is cleared and the Lawson-Hanson path of the general solve kernel, launched afterwards, takes it.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include "dense.cuh"
 #include "solver_core.cuh"
 
@@ -548,26 +549,42 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
         const TIO* pred = pred_all + (size_t)b * d;
 
         // ---- setup
-        double cc = 0.0, l1m = 0.0, dmax = 0.0;
+        double cc = 0.0, l1m = 0.0, dmax = 0.0, dsum = 0.0, osum = 0.0;
+        double* dgv = vec + 3 * p.L.d_pad;                      // [m]  diagonal of G~ (scaling of the binding block)
         for (int k = tid; k < d; k += kDT) { const TIO vc = (TIO)(p.sign * (double)pred[k]); c[k] = vc; r[k] = (double)vc; cc += (double)vc * (double)vc; }
         for (int v = tid; v < mp; v += kDT) {
             const bool in = v < m;
             S.bb[v] = in ? bsrc[v] : 0.0; S.lam[v] = 0.0; S.lamt[v] = 0.0; S.g[v] = in ? -bsrc[v] : 0.0; S.gt[v] = 0.0; S.dir[v] = 0.0;
             S.arow[v] = in ? gen[v].x : 0;
-            if (in) { const double l = (double)l1src[v]; l1m = l > l1m ? l : l1m; const double gd = (double)G[(size_t)v * mp + v]; dmax = gd > dmax ? gd : dmax; }
+            if (in) {
+                const double l = (double)l1src[v]; l1m = l > l1m ? l : l1m;
+                const float* grow = G + (size_t)v * mp;
+                const double gd = (double)grow[v]; dmax = gd > dmax ? gd : dmax; dsum += gd;
+                dgv[v] = gd > 0.0 ? gd : 1.0;
+                // a sample of the off-diagonal magnitudes: how good a model of G~ its diagonal is
+                osum += fabs((double)grow[(v + 1) % m]) + fabs((double)grow[(v + 7) % m]) + fabs((double)grow[(v + m / 2) % m]) + fabs((double)grow[(v + m / 3 + 1) % m]);
+            }
         }
         cc = cx.block_sum(cc);
         cx.block_max2(l1m, dmax);
+        cx.block_sum2(dsum, osum);
+        // Scaling M of the binding block in Bertsekas' two-metric projection: diag(G~)^-1 when G~ is weakly coupled (Gaussian-like
+        // rows: the 1-D Newton step is then the right step for a nearly active variable and epsilon lives in lambda units), the
+        // identity when the rows are strongly correlated (e.g. positive matrices, where almost everything ends up bound and the
+        // aggressive identity-scaled rule identifies it in a few iterations).  An instance switches to the diagonal scaling for good
+        // when a line search has to cut the step to the order of 1 / G_vv (the signature of the identity scaling overshooting).
+        bool scaled = osum * 0.25 < 0.25 * dsum;
         const double cnorm = sqrt(cc);
         const bool finite_in = cc < 1e300;
         DPROF(DP_SETUP);
         int status = ST_BADINPUT, iters = 0;
         bool handed_back = false;
+        int why = 0, why_phase = 0;
         if (finite_in) {
             const double scale = (l1m > 1.0 ? l1m : 1.0) * (cnorm > 1e-30 ? cnorm : 1e-30);
             const double tol = (p.tol > 0 ? p.tol : 1e-12) * scale;
             const double tolG = 1e-6 * scale > tol ? 1e-6 * scale : tol;
-            const int max_it1 = p.max_iter > 0 ? p.max_iter : 60, max_it2 = 24;
+            const int max_it1 = p.max_iter > 0 ? p.max_iter : 60, max_it2 = 40;
             const int max_ls = p.max_ls > 0 ? p.max_ls : 40;
             // Tikhonov term above the accuracy of G~ (3xTF32 operands, truncating float32 accumulation: ~1.5e-5 relative on the
             // diagonal at d = 1225), so that the factored matrix is positive definite even where G_FF is singular (|F| > d)
@@ -583,7 +600,7 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
                 double res = kkt_residual(lam, g, m, cx);
                 DPROF(DP_KKT);
                 if (phase == 1 && (res <= tolG || it1 >= max_it1)) {
-                    if (res > 1e-4 * scale) { handed_back = true; break; }       // the Gram-space iteration did not settle
+                    if (res > 1e-4 * scale) { handed_back = true; why = 1; why_phase = 1; break; }       // the Gram-space iteration did not settle
                     // ---- switch to the true problem: r = c - A^T lam, g = -A r
                     phase = 2; since_best = 0; res_best = 1e300;
                     f = 0.5 * true_residual<TIO>(Ainst, d, m, lam, c, rc, S, cx, &s_cnt);
@@ -597,7 +614,7 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
                     else if (++since_best >= 4 && res <= 1e3 * tol) { status = ST_CONVERGED; break; }
                     if (it2 >= max_it2) {
                         status = res <= 1e3 * tol ? ST_CONVERGED : ST_ITER_CAP;
-                        if (res > 1e-8 * scale) handed_back = true;
+                        if (res > 1e-8 * scale) { handed_back = true; why = 3; why_phase = 2; }
                         break;
                     }
                     ++it2;
@@ -611,7 +628,7 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
                     int cnt = 0; bool same = true;
                     for (int v0 = 0; v0 < m; v0 += 32) {
                         const int v = v0 + cx.lane;
-                        const bool isf = v < m && !(lam[v] <= epsb && g[v] > 0.0);
+                        const bool isf = v < m && !(lam[v] <= (scaled ? epsb / dgv[v] : epsb) && g[v] > 0.0);
                         const unsigned mk = __ballot_sync(0xffffffffu, isf);
                         if (isf) {
                             const int pos = cnt + __popc(mk & ((1u << cx.lane) - 1u));
@@ -623,7 +640,7 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
                     same = __all_sync(0xffffffffu, same) && cnt == nf_fact;
                     if (cx.lane == 0) { s_nf = cnt; s_same = same ? 1 : 0; }
                 }
-                for (int v = tid; v < m; v += kDT) S.dir[v] = g[v];
+                for (int v = tid; v < m; v += kDT) S.dir[v] = scaled ? g[v] / dgv[v] : g[v];
                 __syncthreads();
                 const int nf = s_nf;
                 const bool same = s_same != 0;
@@ -688,13 +705,18 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
                     if (ft <= f - 1e-4 * dec + 4.0 * kEps * fa) { ok = true; break; }
                     alpha *= 0.5;
                 }
+                if (p.trace_b == b && tid == 0)
+                    printf("dense trace b=%d phase %d it1 %d it2 %d res/scale %.3e nf %d same %d alpha %.3e f %.15e ft %.15e ok %d floor %d\n", b, phase, it1, it2,
+                           res / scale, nf, (int)same, alpha, f, ft, (int)ok, (int)at_floor);
+                if (!ok && !scaled) { scaled = true; continue; }      // identity scaling failed outright: retry this point with the diagonal one
                 if (!ok) {
                     // the current point stays; in phase 1 a stall close to the solution still goes on to the true problem
                     if (phase == 1 && res <= 1e-4 * scale) { it1 = max_it1; continue; }
                     status = (phase == 2 && res <= 1e3 * tol) ? ST_CONVERGED : ST_STALLED;
-                    if (phase == 1 || res > 1e-8 * scale) handed_back = true;
+                    if (phase == 1 || res > 1e-8 * scale) { handed_back = true; why = phase == 1 ? 2 : 4; why_phase = phase; }
                     break;
                 }
+                if (alpha < 1.0 / 64.0) scaled = true;
                 { double* t1 = lam; lam = lamt; lamt = t1; }
                 f = ft;
                 if (phase == 1) { double* t2 = g; g = gt; gt = t2; }
@@ -712,6 +734,7 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
             }
             __syncthreads();
         }
+        if (handed_back && p.no_handback) { handed_back = false; status |= (why << 16) | (why_phase << 12); }
         if (handed_back) {
             if (tid == 0) flag[b] = 0;               // the Lawson-Hanson path (general solve kernel, launched next) takes it
         } else if (!finite_in) {                     // NaN / Inf prediction: reported, never a silent number

@@ -15,5 +15,9 @@ for seed in [int(s) for s in sys.argv[4:]] or [1000, 1001]:
     st = out["status"].cpu().numpy(); it = out["iters"].cpu().numpy()
     vals, cnts = np.unique(st, return_counts=True)
     print(f"seed {seed}: {B / dt:.1f} inst/s; status counts {dict(zip([hex(v) for v in vals], cnts.tolist()))}; iters mean {it.mean():.1f} max {it.max()}", flush=True)
-    bad = np.flatnonzero((st & 0x200) == 0)
-    print("   instances off the Gram path:", bad[:20].tolist(), "iters", it[bad][:20].tolist())
+    bad = np.flatnonzero(((st & 0x200) == 0) | ((st >> 12) != 0))
+    print("   instances off the Gram path / flagged:", bad[:20].tolist(), "iters", it[bad][:20].tolist(), "status", [hex(x) for x in st[bad][:20]])
+    if len(bad) and os.environ.get("DUMP"):
+        i = int(bad[0])
+        np.savez_compressed(f"gpurun_out/dense_bad_{seed}_{i}.npz", A=A[i].cpu().numpy(), c=c[i].cpu().numpy(),
+                            proj=cave_forward_backward(c[i:i+1], A[i:i+1], -1.0, 0, 0.0, "none", want_proj=True, dense=False)["proj"].cpu().numpy())

@@ -289,14 +289,17 @@ def run_ours(args):
         g = torch.Generator(device=dev).manual_seed(1000 + rank)
         A = torch.randn((batch, m, d), generator=g, device=dev)
         c = -torch.randn((batch, d), generator=g, device=dev)       # pred_cost; the signed cost is -pred (MINIMIZE, src/cave.py:62-64)
-        step = lambda: cave_forward_backward(c, A, -1.0, 0, 0.0, "mean", precision=args.precision)  # noqa: E731
+        # the host gate of the dense path is `m_max <= d` (structured models have m > d); rows up to 1.7 d still have a
+        # unique solution for Gaussian rows, so the sweep asks for the dense path there explicitly
+        dense = True if (d < m <= 1.7 * d and m >= 128) else "auto"
+        step = lambda: cave_forward_backward(c, A, -1.0, 0, 0.0, "mean", precision=args.precision, dense=dense)  # noqa: E731
         for _ in range(2):
             step()
         ms = timed(step, steps)
-        st = cave_forward_backward(c, A, -1.0, 0, 0.0, "none", precision=args.precision, want_status=True)
+        st = cave_forward_backward(c, A, -1.0, 0, 0.0, "none", precision=args.precision, want_status=True, dense=dense)
         status = st["status"].cpu().numpy()
         flops = float(batch) * (float(m) * m * d + 4.0 * m * d)                # SURVEY 8d "Algorithmic flops"
-        info = {"d": d, "m": m, "batch_per_gpu": batch, "inst_per_s": batch * world / (ms * 1e-3), "ms_per_step": ms,
+        info = {"d": d, "m": m, "batch_per_gpu": batch, "dense_mode": str(dense), "inst_per_s": batch * world / (ms * 1e-3), "ms_per_step": ms,
                 "iters_mean": float(st["iters"].float().mean()),
                 "path_gram_frac": float(((status & _lib.ST_PATH_GRAM) != 0).mean()),
                 "converged_frac": float(((status & 0xff) == 0).mean()),
@@ -512,7 +515,7 @@ def run_ours(args):
                    "batch_per_gpu": B, "m_max": m_max, "d": d, "l2_policy": "inputs larger than L2 (A = %.1f GB)" % (scan_bytes / 1e9)},
         "clocks": clocks, "e2e": e2e, "e2e_sparse_host": e2e_sparse, "e2e_resident_dataset": e2e_resident, "gpu_launches": launches,
         "gpu_launches_note": "kernels launched by libcave_b200.so inside the timed region (cave_launch_count): per step scan, plan, "
-                             "order, four solve configurations of which the device selects one, finalize",
+                             "order, clear-setup, four solve configurations of which the device selects one, finalize",
         "roofline": roofline, "kernels": kernels, "solve_launch_plan": plan_info,
         "solver": {"status_counts": {str(k): int(v) for k, v in zip(*np.unique(status, return_counts=True))},
                    "iters_mean": float(iters.mean()), "iters_max": int(iters.max()), "loss": loss_val},

@@ -246,11 +246,11 @@ static int pack_impl(const float* A, const int32_t* m_rows, int64_t B, int64_t m
     if (!emit_setup) {
         // no cached setup in this pack: the valid word of every instance's setup block must say so (the pack buffer is the
         // caller's uninitialised memory, possibly a recycled pack)
-        e = cudaMemset2DAsync(base + L.setup, (size_t)L.setup_stride, 0, 4, (size_t)B, (cudaStream_t)stream);
-        if (e != cudaSuccess) return fail(CAVE_ECUDA, "cudaMemset2DAsync failed: %s", cudaGetErrorString(e));
+        e = cave::launch_clear_setup(base + L.setup, (long long)L.setup_stride, (int)B, (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(CAVE_ECUDA, "clear-setup kernel launch failed: %s", cudaGetErrorString(e));
     }
     e = cave::launch_plan(pp, (cudaStream_t)stream);
-    g_launches += emit_setup ? 3 : 2;
+    g_launches += 3;      // plan, order, and the setup kernel or the kernel that clears the setup blocks' valid words
     if (e != cudaSuccess) return fail(CAVE_ECUDA, "plan kernel launch failed: %s", cudaGetErrorString(e));
     return CAVE_OK;
 }

@@ -1005,6 +1005,16 @@ __global__ void __launch_bounds__(kSetupThreads) setup_kernel(PlanParams p, int 
     }
 }
 
+__global__ void clear_setup_kernel(char* setup, long long stride, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) *(int*)(setup + (size_t)b * (size_t)stride) = 0;
+}
+// packs without a cached setup: the valid word of every instance's setup block says so
+cudaError_t launch_clear_setup(char* setup, long long stride, int B, cudaStream_t stream) {
+    clear_setup_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(setup, stride, B);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_plan(const PlanParams& p, cudaStream_t stream) {
     plan_kernel<<<dim3((unsigned)((p.B + 7) / 8)), dim3(256), 0, stream>>>(p);
     cudaError_t e = cudaGetLastError();

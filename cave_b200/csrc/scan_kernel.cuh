@@ -42,5 +42,6 @@ struct PlanParams {
     char* setup; int64_t setup_stride, setup_cap_v;
 };
 cudaError_t launch_plan(const PlanParams& p, cudaStream_t stream);
+cudaError_t launch_clear_setup(char* setup, long long stride, int B, cudaStream_t stream);
 
 }  // namespace cave

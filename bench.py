@@ -211,6 +211,10 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs CUDA devices (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if world > 1:           # one process per GPU: keep its pinned host buffers on the GPU's NUMA node (e2e legs)
+        from cave_b200.parallel import bind_to_gpu_numa_node
+        numa = bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -513,7 +517,7 @@ def run_ours(args):
         "config": {"workload": f"{args.workload} DFJ synthetic (SURVEY App. B), CaVE+ inner_ratio {ratio}, batch {B}/GPU, "
                                f"pred regime {args.regime}, dense float32 [B,{m_max},{d}] resident in HBM, cold pack",
                    "batch_per_gpu": B, "m_max": m_max, "d": d, "l2_policy": "inputs larger than L2 (A = %.1f GB)" % (scan_bytes / 1e9)},
-        "clocks": clocks, "e2e": e2e, "e2e_sparse_host": e2e_sparse, "e2e_resident_dataset": e2e_resident, "gpu_launches": launches,
+        "numa_binding": numa, "clocks": clocks, "e2e": e2e, "e2e_sparse_host": e2e_sparse, "e2e_resident_dataset": e2e_resident, "gpu_launches": launches,
         "gpu_launches_note": "kernels launched by libcave_b200.so inside the timed region (cave_launch_count): per step scan, plan, "
                              "order, clear-setup, four solve configurations of which the device selects one, finalize",
         "roofline": roofline, "kernels": kernels, "solve_launch_plan": plan_info,

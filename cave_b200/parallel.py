@@ -36,3 +36,33 @@ def sharded_grad_scale(local_count: int, global_count: int, world: int) -> float
     gradient equals the global-batch mean gradient when shards are equal; for ragged shards multiply the
     local loss by this factor first: (local_count / global_count) * world."""
     return float(local_count) * world / float(max(global_count, 1))
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off (one process per GPU), so that the pinned
+    host buffers it allocates afterwards are local to the GPU's PCIe root and eight ranks do not all stream through one
+    socket's memory controllers.  Best effort: returns what it found / did; never raises."""
+    import os
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node"
+        node = int(open(path).read().strip())
+        info["pci"], info["numa_node"] = bus, node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["bound"], info["cpus"] = True, len(allowed)
+    except Exception as e:      # no sysfs / NVML in this container: leave the affinity alone
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info

@@ -264,8 +264,9 @@ def run_ours(args):
         n = len(work)
         l_ref = np.array([r[0] for r in res]); g_ref = np.stack([r[1] for r in res])
         l_gpu = loss_i[:n].double().cpu().numpy(); g_gpu = grad[:n].double().cpu().numpy()
-        return {"n": n, "max_rel_err_loss": float(np.abs(l_gpu - l_ref).max() / max(np.abs(l_ref).max(), 1e-30)),
-                "max_rel_err_grad": float(np.abs(g_gpu - g_ref).max() / max(np.abs(g_ref).max(), 1e-30)),
+        # relative to the largest reference entry, floored: a cone that is the whole space has loss = 0 and gradient = 0 exactly
+        return {"n": n, "max_rel_err_loss": float(np.abs(l_gpu - l_ref).max() / max(np.abs(l_ref).max(), 1e-6)),
+                "max_rel_err_grad": float(np.abs(g_gpu - g_ref).max() / max(np.abs(g_ref).max(), 1e-6)),
                 "note": "GPU (this run's precision mode, float32 I/O) vs oracle.forward_backward in the reference's dtypes on the first n "
                         "instances of the timed batch; computed outside the timed region"}
 
@@ -370,8 +371,22 @@ def run_ours(args):
 
     # ---- per-kernel timings for the roofline (same stream, CUDA events, same inputs)
     pack = pack_constraints(A)
-    ms_scan = timed(lambda: pack_constraints(A, cache_setup=False), max(3, args.steps // 2))     # scan + plan + order: what a cold step runs
-    ms_pack = timed(lambda: pack_constraints(A), max(3, args.steps // 2))                         # + the setup kernel (reusable packs)
+    # the pack pass alone, through the C ABI into one preallocated buffer (no allocator traffic inside the timed region):
+    # flags 0 = scan + plan + order (+ clearing the setup words): what a cold step runs; flags 1 = + the setup kernel
+    import ctypes
+    nb_pack = ctypes.c_size_t()
+    _lib.check(lib.cave_pack_bytes(B, m_max, d, ctypes.byref(nb_pack)))
+    pbuf = torch.empty(nb_pack.value, dtype=torch.uint8, device=dev)
+    cur_stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def pack_pass(flags):
+        _lib.check(lib.cave_pack_ex(ctypes.c_void_p(A.data_ptr()), None, B, m_max, d, flags, ctypes.c_void_p(pbuf.data_ptr()),
+                                    nb_pack.value, cur_stream))
+
+    pack_pass(0); pack_pass(1)
+    ms_scan = timed(lambda: pack_pass(0), max(3, args.steps // 2))
+    ms_pack = timed(lambda: pack_pass(1), max(3, args.steps // 2))
+    del pbuf
     warm = lambda: cave_forward_backward(pred, A, -1.0, mode, ratio, "mean", precision=args.precision, pack=pack)  # noqa: E731
     warm()
     ms_solve = timed(warm, max(3, args.steps // 2))

@@ -444,29 +444,20 @@ __device__ double true_residual(const float* __restrict__ Ainst, int d, int m, c
     return cx.block_sum(ff);        // (barriers inside: rout is visible afterwards)
 }
 
-// g = -A r over all rows: one warp per pair of rows, 2 x 16 four-byte loads in flight per lane (the rows are 4-byte aligned only)
+// g = -A r over all rows (one warp per row, sixteen 4-byte loads in flight per lane)
 __device__ void true_gradient(const float* __restrict__ Ainst, int d, int m, const double* r, double* g, const DenseSmem& S, Ctx& cx) {
-    for (int v0 = 2 * cx.warp; v0 < m; v0 += 2 * cx.nwarp) {
-        const bool two = v0 + 1 < m;
-        const float* row0 = Ainst + (size_t)S.arow[v0] * d;
-        const float* row1 = Ainst + (size_t)S.arow[two ? v0 + 1 : v0] * d;
-        double acc0 = 0.0, acc1 = 0.0;
+    for (int v = cx.warp; v < m; v += cx.nwarp) {
+        const float* row = Ainst + (size_t)S.arow[v] * d;
+        double acc = 0.0;
         for (int k0 = 0; k0 < d; k0 += 512) {
-            float a0[16], a1[16];
+            float a[16];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const int k = k0 + u * 32 + cx.lane;
-                a0[u] = k < d ? __ldg(row0 + k) : 0.f;
-                a1[u] = k < d ? __ldg(row1 + k) : 0.f;
-            }
+            for (int u = 0; u < 16; ++u) { const int k = k0 + u * 32 + cx.lane; a[u] = k < d ? __ldg(row + k) : 0.f; }
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const int k = k0 + u * 32 + cx.lane;
-                if (k < d) { const double rk = r[k]; acc0 += (double)a0[u] * rk; acc1 += (double)a1[u] * rk; }
-            }
+            for (int u = 0; u < 16; ++u) { const int k = k0 + u * 32 + cx.lane; if (k < d) acc += (double)a[u] * r[k]; }
         }
-        acc0 = cx.warp_sum(acc0); acc1 = cx.warp_sum(acc1);
-        if (cx.lane == 0) { g[v0] = -acc0; if (two) g[v0 + 1] = -acc1; }
+        acc = cx.warp_sum(acc);
+        if (cx.lane == 0) g[v] = -acc;
     }
     __syncthreads();
 }

@@ -309,7 +309,7 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
 
     cudaStream_t st = (cudaStream_t)stream;
     if (!(opts && opts->warm_pack)) {
-        if (int e = pack_impl(A, m_rows, B, m_max, d, pack, pack_bytes, stream, false)) return e;
+        if (int e = pack_impl(A, m_rows, B, m_max, d, pack, pack_bytes, stream, env_int("CAVE_COLD_SETUP", 0) != 0)) return e;
     }
     char* pb = (char*)pack;
     char* sb = (char*)scratch;
@@ -337,7 +337,7 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
     sp.plan = (const unsigned long long*)(pb + PL.plan);
     sp.order = (indexed || env_int("CAVE_SOLVE_ORDER", 1) == 0) ? nullptr : (const int*)(pb + PL.order);       // the order of a dataset-wide pack does not apply to a batch
     sp.n_packed = Bpack;
-    sp.setup = (opts && opts->warm_pack && env_int("CAVE_SETUP_CACHE", 1)) ? pb + PL.setup : nullptr;
+    sp.setup = (((opts && opts->warm_pack) || env_int("CAVE_COLD_SETUP", 0)) && env_int("CAVE_SETUP_CACHE", 1)) ? pb + PL.setup : nullptr;
     sp.setup_stride = PL.setup_stride;
     sp.dense_flag = nullptr;
     if (dense) {

@@ -52,28 +52,13 @@ __host__ __device__ inline size_t dense_solve_smem(int64_t m_pad) {
     return o + 256;
 }
 
-// ---- 32 x 32 Cholesky by one warp: lane i holds row i of the lower triangle in registers.  On return lane i holds row i
-// of L (diagonal included); pivots are floored.
-__device__ __forceinline__ void chol32_warp(float (&a)[32], int lane, float floor_) {
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-        const float piv = __shfl_sync(0xffffffffu, a[c], c);
-        const float l = sqrtf(piv > floor_ ? piv : floor_);
-        const float inv = 1.0f / l;
-        const float mine = lane == c ? l : a[c] * inv;
-        a[c] = mine;
-#pragma unroll
-        for (int j = c + 1; j < 32; ++j) {
-            const float ljc = __shfl_sync(0xffffffffu, mine, j);
-            a[j] = fmaf(-mine, ljc, a[j]);          // rows i >= j use it; others hold garbage above the diagonal
-        }
-    }
-}
-
-// Factor the kNB x kNB diagonal block held in D (row stride kNB + 1, lower triangle valid) in place; nb valid rows.
-// All threads call; ends with a barrier.  invd[c] = 1 / L[c][c].
+// Factor the kNB x kNB diagonal block held in D (row stride kNB + 1, lower triangle valid, zero above it) in place; nb valid
+// rows.  Right-looking in panels of 8 columns: warp 0 factors a panel entirely in registers (rows lane and lane + 32, the
+// pivot row broadcast by shuffles, rsqrt pivots), then all warps apply the rank-8 update to the trailing block — two CTA
+// barriers per panel and no 32-step dependent chain.  Entries above the diagonal collect garbage in the registers; they are
+// never stored.  All threads call; ends with a barrier.  invd[c] = 1 / L[c][c].
 __device__ void factor_diag(float* D, float* invd, int nb, float floor_, int tid) {
-    constexpr int LD = kNB + 1;
+    constexpr int LD = kNB + 1, PB = 8;
     const int lane = tid & 31, warp = tid >> 5;
     // rows / columns >= nb: identity, so the 64-wide code below needs no bounds
     for (int t = tid; t < kNB * kNB; t += kDT) {
@@ -81,55 +66,52 @@ __device__ void factor_diag(float* D, float* invd, int nb, float floor_, int tid
         if (i >= nb || j >= nb) D[i * LD + j] = i == j ? 1.0f : 0.0f;
     }
     __syncthreads();
-    if (warp == 0) {                                    // D11
-        float a[32];
+    for (int j0 = 0; j0 < kNB; j0 += PB) {
+        if (warp == 0) {
+            const bool hi = j0 >= 32;                   // a panel never straddles row 32: its pivot rows sit in one register set
+            float a0[PB], a1[PB];                       // rows lane and lane + 32
 #pragma unroll
-        for (int j = 0; j < 32; ++j) a[j] = j <= lane ? D[lane * LD + j] : 0.0f;
-        chol32_warp(a, lane, floor_);
+            for (int c = 0; c < PB; ++c) {
+                a0[c] = lane >= j0 ? D[lane * LD + j0 + c] : 0.0f;
+                a1[c] = D[(lane + 32) * LD + j0 + c];
+            }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (j <= lane) D[lane * LD + j] = a[j];
-    }
-    __syncthreads();
-    // invd of the first block: lane holds a[lane] only by dynamic index; recompute from memory
-    if (tid < 32) invd[tid] = 1.0f / D[tid * LD + tid];
-    __syncthreads();
-    if (tid < 32) {                                     // D21 <- D21 L11^-T : one thread per row 32 + tid
-        float x[32];
-        const int r = 32 + tid;
+            for (int jj = 0; jj < PB; ++jj) {
+                const int j = j0 + jj;
+                const float piv = __shfl_sync(0xffffffffu, hi ? a1[jj] : a0[jj], j & 31);
+                const float pv = piv > floor_ ? piv : floor_;
+                float inv = rsqrtf(pv);
+                inv = inv * (1.5f - 0.5f * pv * inv * inv);         // one Newton step: full float32 accuracy
+                const float l = pv * inv;
+                if (lane == 0) invd[j] = inv;
+                a0[jj] = (lane == j) ? l : a0[jj] * inv;
+                a1[jj] = (lane + 32 == j) ? l : a1[jj] * inv;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = D[r * LD + j];
+                for (int c = jj + 1; c < PB; ++c) {
+                    const float t = __shfl_sync(0xffffffffu, hi ? a1[jj] : a0[jj], (j0 + c) & 31);   // L[j0 + c][j]
+                    a0[c] = fmaf(-a0[jj], t, a0[c]);
+                    a1[c] = fmaf(-a1[jj], t, a1[c]);
+                }
+            }
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            float s = x[c];
-#pragma unroll
-            for (int q = 0; q < c; ++q) s = fmaf(-x[q], D[c * LD + q], s);
-            x[c] = s * invd[c];
+            for (int c = 0; c < PB; ++c) {
+                if (lane >= j0 + c) D[lane * LD + j0 + c] = a0[c];
+                if (lane + 32 >= j0 + c) D[(lane + 32) * LD + j0 + c] = a1[c];
+            }
         }
+        __syncthreads();
+        const int t0 = j0 + PB, n = kNB - t0;           // trailing block: D[i][k] -= sum_c L[i][j0 + c] L[k][j0 + c], k <= i
+        for (int t = tid; t < n * n; t += kDT) {
+            const int i = t0 + t / n, k = t0 + t % n;
+            if (k <= i) {
+                float acc = D[i * LD + k];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) D[r * LD + j] = x[j];
-    }
-    __syncthreads();
-    for (int t = tid; t < 32 * 32; t += kDT) {          // D22 -= D21 D21^T (lower triangle)
-        const int i = t >> 5, j = t & 31;
-        if (j <= i) {
-            float s = D[(32 + i) * LD + 32 + j];
-#pragma unroll 8
-            for (int q = 0; q < 32; ++q) s = fmaf(-D[(32 + i) * LD + q], D[(32 + j) * LD + q], s);
-            D[(32 + i) * LD + 32 + j] = s;
+                for (int c = 0; c < PB; ++c) acc = fmaf(-D[i * LD + j0 + c], D[k * LD + j0 + c], acc);
+                D[i * LD + k] = acc;
+            }
         }
+        __syncthreads();
     }
-    __syncthreads();
-    if (warp == 0) {                                    // D22
-        float a[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) a[j] = j <= lane ? D[(32 + lane) * LD + 32 + j] : 0.0f;
-        chol32_warp(a, lane, floor_);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (j <= lane) D[(32 + lane) * LD + 32 + j] = a[j];
-    }
-    __syncthreads();
-    if (tid < 32) invd[32 + tid] = 1.0f / D[(32 + tid) * LD + 32 + tid];
-    __syncthreads();
 }
 
 // One chunk of the block-column update of the left-looking Cholesky: rows [r0, r0 + 64 RM) x columns [j0, j0 + 64) of W get

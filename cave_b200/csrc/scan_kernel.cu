@@ -979,23 +979,46 @@ __global__ void __launch_bounds__(kSetupThreads) setup_kernel(PlanParams p, int 
     __syncthreads();
     for (int k = tid; k <= d; k += kSetupThreads) { o_cptr[k] = cnt[k]; if (k < d) cur[k] = cnt[k]; }
     __syncthreads();
-    for (int v = warp; v < nv; v += NW) {
-        const int src = goff[keep[v]], n = rp[v + 1] - rp[v];
-        for (int e = lane; e < n; e += 32) {
-            const int q = atomicAdd(&cur[pcol[src + e]], 1);
-            o_crow[q] = (uint16_t)v; o_cval[q] = (signed char)pval[src + e];
-        }
-    }
-    __syncthreads();                    // (global writes of this CTA are visible to it after the barrier)
-    for (int k = tid; k < d; k += kSetupThreads) {          // insertion sort of every short column: deterministic order
-        const int s0 = cnt[k], e0 = cnt[k + 1];
-        if (e0 - s0 <= 64)
-            for (int a = s0 + 1; a < e0; ++a) {
-                const uint16_t rr = o_crow[a]; const signed char vv = o_cval[a];
-                int q = a - 1;
-                while (q >= s0 && o_crow[q] > rr) { o_crow[q + 1] = o_crow[q]; o_cval[q + 1] = o_cval[q]; --q; }
-                o_crow[q + 1] = rr; o_cval[q + 1] = vv;
+    // CSC fill, ordered by construction: every warp owns a range of columns and walks the kept rows in ascending variable
+    // order, placing the entries whose column falls into its range (the columns of one row are distinct, so the cursors need
+    // no atomics and every column comes out sorted by variable: no sort, a fixed summation order for the solver).  The next
+    // row's entries are fetched while the current one is placed (rows of up to 256 non-zeros; longer rows take the loop).
+    {
+        const int c_lo = (int)(((long long)d * warp) / NW), c_hi = (int)(((long long)d * (warp + 1)) / NW);
+        constexpr int U = 8;
+        int cc[U]; float vv[U];
+        auto fetch = [&](int v) {
+            const int src = goff[keep[v]], n = rp[v + 1] - rp[v];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = lane + 32 * u;
+                cc[u] = e < n ? (int)pcol[src + e] : -1;
+                vv[u] = e < n ? pval[src + e] : 0.f;
             }
+        };
+        if (nv > 0) fetch(0);
+        for (int v = 0; v < nv; ++v) {
+            int c0[U]; float v0[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { c0[u] = cc[u]; v0[u] = vv[u]; }
+            const int n = rp[v + 1] - rp[v];
+            if (v + 1 < nv) fetch(v + 1);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (c0[u] >= c_lo && c0[u] < c_hi) {
+                    const int q = cur[c0[u]]; cur[c0[u]] = q + 1;
+                    o_crow[q] = (uint16_t)v; o_cval[q] = (signed char)v0[u];
+                }
+            }
+            if (n > 32 * U) {
+                const int src = goff[keep[v]];
+                for (int e = 32 * U + lane; e < n; e += 32) {
+                    const int c = pcol[src + e];
+                    if (c >= c_lo && c < c_hi) { const int q = cur[c]; cur[c] = q + 1; o_crow[q] = (uint16_t)v; o_cval[q] = (signed char)pval[src + e]; }
+                }
+            }
+            __syncwarp();
+        }
     }
     if (tid == 0) {
         hdr[1] = nv; hdr[2] = nz;

@@ -366,3 +366,16 @@ def test_launch_plan_tracks_the_instance_size():
     A, _ = synth.dense_batch(4, 256, 190, seed=5, device=dev)
     dense = pack_constraints(A.contiguous()).launch_plan("fp64")
     assert dense["config"] == 3
+
+
+def test_tsp50_benchmark_regime_sample_matches_oracle():
+    """The benchmarked workload itself (TSP-50, uniform predictions, generator seed 1000 as in bench.py): the first instances
+    of the timed batch against the oracle, fp64 and fp32-factor modes (VERDICT round 1, weak point 2)."""
+    from cave_b200 import synth
+    insts = synth.make_batch("tsp50", 8, seed=1000)
+    ctrs = synth.densify(insts).numpy()
+    pred = synth.predictions(insts, 1000, "uniform")
+    ref = O.forward_backward(pred, ctrs, mode=1, inner_ratio=0.2, reduction="none", fp64=True)
+    for precision in ("fp64", "fp32"):
+        out = _run(pred, ctrs, mode=1, inner_ratio=0.2, reduction="none", precision=precision)
+        _check(out, ref, RTOL[precision], 1)

@@ -137,8 +137,8 @@ int64_t dense_slots(const cave_solver_opts* o, int64_t B, int64_t m_max, int64_t
     if (o && o->dense_slots > 0) n = o->dense_slots;
     else {
         const int64_t sms = sm_count();
-        const int64_t by_budget = (int64_t)(((size_t)12 << 30) / cave::dense_slot_bytes(m_max, d));
-        n = 4 * sms < by_budget ? 4 * sms : by_budget;
+        const int64_t by_budget = (int64_t)(((size_t)24 << 30) / cave::dense_slot_bytes(m_max, d));
+        n = 8 * sms < by_budget ? 8 * sms : by_budget;       // more instances per round: a shorter relative tail in the solve kernel
         if (n < sms) n = sms;
     }
     return n < B ? n : B;

@@ -87,7 +87,7 @@ typedef struct cave_solver_opts {
     const int32_t* inst_index;
     int64_t n_packed;        /* 0 / ignored unless inst_index is set                                   */
     int64_t dense_slots;     /* dense path: instances whose Gram workspace is resident at once (the batch is processed
-                                in ceil(B / dense_slots) rounds); <= 0 -> default (4 per SM, at most ~12 GiB)      */
+                                in ceil(B / dense_slots) rounds); <= 0 -> default (8 per SM, at most ~24 GiB)      */
 } cave_solver_opts;
 
 typedef struct cave_limits {

@@ -267,6 +267,7 @@ def run_ours(args):
         # relative to the largest reference entry, floored: a cone that is the whole space has loss = 0 and gradient = 0 exactly
         return {"n": n, "max_rel_err_loss": float(np.abs(l_gpu - l_ref).max() / max(np.abs(l_ref).max(), 1e-6)),
                 "max_rel_err_grad": float(np.abs(g_gpu - g_ref).max() / max(np.abs(g_ref).max(), 1e-6)),
+                "max_abs_err_grad": float(np.abs(g_gpu - g_ref).max()), "max_abs_grad_ref": float(np.abs(g_ref).max()),
                 "note": "GPU (this run's precision mode, float32 I/O) vs oracle.forward_backward in the reference's dtypes on the first n "
                         "instances of the timed batch; computed outside the timed region"}
 

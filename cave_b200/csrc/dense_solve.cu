@@ -121,68 +121,88 @@ __device__ void factor_diag(float* D, float* invd, int nb, float floor_, int tid
 template <int RM>
 __device__ __forceinline__ void chol_update_chunk(float* __restrict__ W, int ldw, int nf, int j0, int r0, const DenseSmem& S, int tid) {
     constexpr int ROWS = 64 * RM;
-    const int tr = tid & 63, tcg = tid >> 6;
+    // warp tile = 8 row groups x 4 column groups (not 32 x 1): the four 128-bit operand loads of a k-step then touch 128 + 128 +
+    // 64 + 64 distinct bytes per warp (lanes that share an address are served by one multicast) instead of 2 x 512 + 2 x 16
+    const int warp_ = tid >> 5, lane_ = tid & 31;
+    const int tr = (warp_ & 7) * 8 + (lane_ & 7), tcg = (warp_ >> 3) * 4 + (lane_ >> 3);
     float acc[RM][8];
 #pragma unroll
     for (int i = 0; i < RM; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
-    const bool stage_a = tid < ROWS, stage_b = tid < 64;
-    const int myrow = r0 + tid < nf ? r0 + tid : nf - 1;                // staging: one row per thread (clamped)
-    const int mybrow = j0 + (tid & 63) < nf ? j0 + (tid & 63) : nf - 1;
+    // staging: the A operand one row per thread (16 k-values), the 64 x 16 B operand two values per thread (all threads), so
+    // that the prefetch costs 18 registers and the k-loop can keep the next step's operands in flight
+    const bool stage_a = tid < ROWS;
+    const int myrow = r0 + tid < nf ? r0 + tid : nf - 1;                // clamped
+    const int bq_row = tid >> 3, bq_k = (tid & 7) * 2;
+    const int mybrow = j0 + bq_row < nf ? j0 + bq_row : nf - 1;
     const float* arow = W + (size_t)myrow * ldw;
-    const float* brow = W + (size_t)mybrow * ldw;
-    float4 pa[4], pb[4];
+    const float* brow = W + (size_t)mybrow * ldw + bq_k;
+    // Prefetch ring of PD k-slabs in registers: a slab's loads have PD compute phases to arrive.  The loads come from L2 / HBM
+    // (~4000 cycles under load), a compute phase is 4096 / 2048 / 1024 / 512 FFMA-cycles for RM = 8 / 4 / 2 / 1: with a
+    // distance of one slab the short tiles ran at the pace of the memory latency, not of the arithmetic.
+    constexpr int PD = RM == 8 ? 1 : (RM == 4 ? 2 : 4);
+    float4 pa[PD][4]; float2 pb[PD];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        pa[u] = stage_a ? *reinterpret_cast<const float4*>(arow + u * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        pb[u] = stage_b ? *reinterpret_cast<const float4*>(brow + u * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sl = 0; sl < PD; ++sl) {
+        if (sl * kKS < j0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) pa[sl][u] = stage_a ? *reinterpret_cast<const float4*>(arow + sl * kKS + u * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            pb[sl] = *reinterpret_cast<const float2*>(brow + sl * kKS);
+        }
     }
-    for (int p0 = 0; p0 < j0; p0 += kKS) {
-        __syncthreads();                    // previous slab consumed
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (stage_a) {
-                S.As[(u * 4 + 0) * kRC + tid] = pa[u].x; S.As[(u * 4 + 1) * kRC + tid] = pa[u].y;
-                S.As[(u * 4 + 2) * kRC + tid] = pa[u].z; S.As[(u * 4 + 3) * kRC + tid] = pa[u].w;
-            }
-            if (stage_b) {
-                S.Bs[(u * 4 + 0) * kNB + tid] = pb[u].x; S.Bs[(u * 4 + 1) * kNB + tid] = pb[u].y;
-                S.Bs[(u * 4 + 2) * kNB + tid] = pb[u].z; S.Bs[(u * 4 + 3) * kNB + tid] = pb[u].w;
-            }
+    auto load_ops = [&](int k, float (&av)[RM], float (&bv)[8]) {
+        if (RM == 8) {
+            const float4 a0 = *reinterpret_cast<const float4*>(S.As + k * kRC + tr * 4);
+            const float4 a1 = *reinterpret_cast<const float4*>(S.As + k * kRC + 256 + tr * 4);
+            av[0] = a0.x; av[1 % RM] = a0.y; av[2 % RM] = a0.z; av[3 % RM] = a0.w;
+            av[4 % RM] = a1.x; av[5 % RM] = a1.y; av[6 % RM] = a1.z; av[7 % RM] = a1.w;
+        } else if (RM == 4) {
+            const float4 a0 = *reinterpret_cast<const float4*>(S.As + k * kRC + tr * 4);
+            av[0] = a0.x; av[1 % RM] = a0.y; av[2 % RM] = a0.z; av[3 % RM] = a0.w;
+        } else if (RM == 2) {
+            const float2 a0 = *reinterpret_cast<const float2*>(S.As + k * kRC + tr * 2);
+            av[0] = a0.x; av[1 % RM] = a0.y;
+        } else {
+            av[0] = S.As[k * kRC + tr];
         }
-        __syncthreads();
-        if (p0 + kKS < j0) {
+        const float4 b0 = *reinterpret_cast<const float4*>(S.Bs + k * kNB + tcg * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(S.Bs + k * kNB + tcg * 8 + 4);
+        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+    };
+    for (int p0 = 0; p0 < j0; p0 += kKS * PD) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (stage_a) pa[u] = *reinterpret_cast<const float4*>(arow + p0 + kKS + u * 4);
-                if (stage_b) pb[u] = *reinterpret_cast<const float4*>(brow + p0 + kKS + u * 4);
+        for (int sl = 0; sl < PD; ++sl) {
+            const int p = p0 + sl * kKS;
+            if (p < j0) {                       // (uniform across the CTA)
+                __syncthreads();                // previous slab consumed
+                if (stage_a) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        S.As[(u * 4 + 0) * kRC + tid] = pa[sl][u].x; S.As[(u * 4 + 1) * kRC + tid] = pa[sl][u].y;
+                        S.As[(u * 4 + 2) * kRC + tid] = pa[sl][u].z; S.As[(u * 4 + 3) * kRC + tid] = pa[sl][u].w;
+                    }
+                }
+                S.Bs[bq_k * kNB + bq_row] = pb[sl].x; S.Bs[(bq_k + 1) * kNB + bq_row] = pb[sl].y;
+                __syncthreads();
+                if (p + PD * kKS < j0) {
+                    if (stage_a) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) pa[sl][u] = *reinterpret_cast<const float4*>(arow + p + PD * kKS + u * 4);
+                    }
+                    pb[sl] = *reinterpret_cast<const float2*>(brow + p + PD * kKS);
+                }
+                float av[2][RM], bv[2][8];
+                load_ops(0, av[0], bv[0]);
+#pragma unroll
+                for (int k = 0; k < kKS; ++k) {
+                    if (k + 1 < kKS) load_ops(k + 1, av[(k + 1) & 1], bv[(k + 1) & 1]);       // next step's operands while this one multiplies
+#pragma unroll
+                    for (int i = 0; i < RM; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[k & 1][i], bv[k & 1][j], acc[i][j]);
+                }
             }
-        }
-#pragma unroll
-        for (int k = 0; k < kKS; ++k) {
-            float av[RM];
-            if (RM == 8) {
-                const float4 a0 = *reinterpret_cast<const float4*>(S.As + k * kRC + tr * 4);
-                const float4 a1 = *reinterpret_cast<const float4*>(S.As + k * kRC + 256 + tr * 4);
-                av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
-                av[4 % RM] = a1.x; av[5 % RM] = a1.y; av[6 % RM] = a1.z; av[7 % RM] = a1.w;
-            } else if (RM == 4) {
-                const float4 a0 = *reinterpret_cast<const float4*>(S.As + k * kRC + tr * 4);
-                av[0] = a0.x; av[1 % RM] = a0.y; av[2 % RM] = a0.z; av[3 % RM] = a0.w;
-            } else if (RM == 2) {
-                const float2 a0 = *reinterpret_cast<const float2*>(S.As + k * kRC + tr * 2);
-                av[0] = a0.x; av[1 % RM] = a0.y;
-            } else {
-                av[0] = S.As[k * kRC + tr];
-            }
-            const float4 b0 = *reinterpret_cast<const float4*>(S.Bs + k * kNB + tcg * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(S.Bs + k * kNB + tcg * 8 + 4);
-            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int i = 0; i < RM; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
     }
     // ---- W[r, j0 + c] -= acc

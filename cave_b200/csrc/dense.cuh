@@ -98,6 +98,7 @@ struct DenseParams {
     int max_iter, max_ls; double tol;
     int io_f32;
     int nk;                     // d_pad / 32
+    int tc_update;              // set by launch_dense_solve: the Cholesky block-column update runs on the tensor cores (shared memory permitting)
 };
 
 cudaError_t launch_dense_list(const DenseParams& p, cudaStream_t stream);

@@ -15,7 +15,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "dense.cuh"
+#include "tc05.cuh"
 #include "solver_core.cuh"
 
 namespace cave {
@@ -42,12 +44,34 @@ struct DenseSmem {
 #define CPROF(ph) do {} while (0)
 #endif
 
-__host__ __device__ inline size_t dense_solve_smem(int64_t m_pad) {
+// tensor-core update: operand planes of one 32-wide k-slab, K-major with the 128-byte swizzle of the UMMA descriptors:
+// A hi / lo (256 rows x 128 bytes each), B hi / lo (64 rows)
+#ifndef CAVE_TC_INLINE
+#define CAVE_TC_INLINE __noinline__
+#endif
+#ifndef CAVE_TC_PD
+#define CAVE_TC_PD 1
+#endif
+#ifndef CAVE_TC_L2AHEAD
+#define CAVE_TC_L2AHEAD 3
+#endif
+constexpr int kTcL2Ahead = CAVE_TC_L2AHEAD;     // items whose operands are pulled into the L2 ahead of the register prefetch
+// State of the tensor-core update in static shared memory (no kernel-lifetime registers: the solver's matvec loops sit at the
+// register limit): mbarrier of the tcgen05.commit, its phase, TMEM base address (256 columns).
+__shared__ uint64_t tc_bar_s;
+__shared__ uint32_t tc_phase_s, tmem_base_s;
+constexpr int kTcRows = 256;
+constexpr int kTcA = kTcRows * 128;
+constexpr int kTcB = kNB * 128;
+constexpr int kTcBytes = 2 * kTcA + 2 * kTcB;
+constexpr int kStageSimt = (kKS * kRC + kKS * kNB) * 4;      // As, Bs of the FFMA update
+
+__host__ __device__ inline size_t dense_solve_smem(int64_t m_pad, bool tc) {
     size_t o = 0;
     o += 7 * (size_t)m_pad * 8;                 // lam lamt g gt dir bb lamp
     o += 4 * (size_t)m_pad * 4;                 // free lists, arow, sup
     o += (size_t)m_pad * 4;                     // xs
-    o += (size_t)kKS * kRC * 4 + (size_t)kKS * kNB * 4;     // As, Bs
+    o += tc ? (size_t)kTcBytes + 1024 : (size_t)kStageSimt;     // As, Bs / the tensor-core operand planes over them
     o += (size_t)kNB * (kNB + 1) * 4 + (size_t)kNB * kNB * 4 + kNB * 4; // D, Dt, invd
     return o + 256;
 }
@@ -220,7 +244,137 @@ __device__ __forceinline__ void chol_update_chunk(float* __restrict__ W, int ldw
     }
 }
 
+// The same update on the tensor cores (3 x TF32, float32 accumulation in TMEM): rows [r0, r0 + rows), rows <= 512, as up to
+// four 128-row tiles (two per 256-row half; the halves share the staging planes and follow each other in one pipeline).  Per 32-wide k-slab all threads split their 16-byte pieces of L[rows, k..k+32) and L[j0.., k..k+32) into
+// hi / lo TF32 planes, written K-major with the 128-byte swizzle the UMMA descriptor expects (16-byte chunk index XOR row & 7;
+// a quarter-warp writes one full 128-byte row: conflict-free); one thread then issues 4 k-steps x (lo*hi + hi*lo + hi*hi) per
+// tile and commits to the mbarrier; the next slab's global loads are in flight meanwhile and its stores wait for the commit.
+// Epilogue: every warp reads its TMEM lane quarter (tcgen05.ld 32x32b.x32) and subtracts from W.  All threads call.
+__device__ __forceinline__ void tc_store_split(unsigned char* hi, unsigned char* lo, int row, int chunk, const float4& v) {
+    const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+    float4 h, l;
+    h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+    l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+}
+
+// Not inlined: its registers then do not compete with the solver's live state.
+__device__ CAVE_TC_INLINE void chol_update_tc(float* __restrict__ W, int ldw, int nf, int j0, int r0, int rows, float* stage, int tid) {
+    unsigned char* tcbuf = (unsigned char*)(((uintptr_t)stage + 1023) & ~(uintptr_t)1023);
+    uint64_t* tc_bar = &tc_bar_s;
+    uint32_t phase = tc_phase_s;
+    const uint32_t tmem = tmem_base_s;
+    // Work items = (256-row half, k-slab).  The factors of the instances in flight (148 x 1.25 MB) do not fit the L2 and a load
+    // from HBM takes ~4000 cycles under load while an item computes for ~1000: operands are pulled into the L2 kTcL2Ahead items
+    // ahead (prefetch.global.L2, no registers) and into registers PD items ahead.
+    constexpr int PD = CAVE_TC_PD;
+    const int nslab = j0 >> 5;
+    const int nh = (rows + kTcRows - 1) / kTcRows;
+    const int nitem = nh * nslab;
+    const int srow = tid >> 3, chunk = tid & 7;
+    unsigned char* Ah = tcbuf; unsigned char* Al = Ah + kTcA; unsigned char* Bh = Al + kTcA; unsigned char* Bl = Bh + kTcB;
+    const int rb = j0 + srow < nf ? j0 + srow : nf - 1;
+    const float* bsrc = W + (size_t)rb * ldw + chunk * 4;
+    const uint32_t idesc = tc::instr_desc(kNB);
+    auto tiles_of = [&](int h) { const int rh = rows - h * kTcRows; return rh > 128 ? 2 : 1; };
+    // item -> this thread's 16-byte pieces; pf: only an L2 prefetch (every 32-byte sector once: even chunks)
+    auto fetch = [&](int it, float4 (&a)[4], float4& b, bool pf) {
+        const int h = it >= nslab ? 1 : 0, s = it - h * nslab;
+        const int na = tiles_of(h) * 2;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (u < na) {
+                int r = r0 + h * kTcRows + srow + u * 64;
+                r = r < nf ? r : nf - 1;                // clamped: finite operands, the rows are not stored
+                const float* src = W + (size_t)r * ldw + chunk * 4 + s * 32;
+                if (!pf) a[u] = *reinterpret_cast<const float4*>(src);
+                else if (!(chunk & 1)) asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+            }
+        }
+        if (!pf) b = *reinterpret_cast<const float4*>(bsrc + s * 32);
+        else if (!(chunk & 1) && h == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(bsrc + s * 32));
+    };
+    float4 pa[PD][4], pb[PD];
+#pragma unroll
+    for (int sl = 0; sl < PD; ++sl)
+        if (sl < nitem) fetch(sl, pa[sl], pb[sl], false);
+    for (int it = PD; it < PD + kTcL2Ahead && it < nitem; ++it) fetch(it, pa[0], pb[0], true);
+    for (int it0 = 0; it0 < nitem; it0 += PD) {
+#pragma unroll
+        for (int sl = 0; sl < PD; ++sl) {
+            const int it = it0 + sl;
+            if (it < nitem) {                                                   // (uniform across the CTA)
+                const int h = it >= nslab ? 1 : 0, s = it - h * nslab;
+                const int nt = tiles_of(h);
+                if (it > 0) { tc::mbar_wait(tc_bar, phase); phase ^= 1u; }    // the MMAs of the previous item have read the planes
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (u < nt * 2) tc_store_split(Ah, Al, srow + u * 64, chunk, pa[sl][u]);
+                tc_store_split(Bh, Bl, srow, chunk, pb[sl]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+                if (tid == 0) {
+                    tc::fence_after();
+                    const uint32_t aH = tc::smem_u32(Ah), aL = tc::smem_u32(Al), bH = tc::smem_u32(Bh), bL = tc::smem_u32(Bl);
+                    for (int t = 0; t < nt; ++t) {
+                        const uint32_t dcol = tmem + (uint32_t)(h * 2 + t) * kNB;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t dAh = tc::smem_desc(aH + t * 16384 + kk * 32), dAl = tc::smem_desc(aL + t * 16384 + kk * 32);
+                            const uint64_t dBh = tc::smem_desc(bH + kk * 32), dBl = tc::smem_desc(bL + kk * 32);
+                            tc::mma_tf32(dcol, dAl, dBh, idesc, (s | kk) != 0 ? 1u : 0u);
+                            tc::mma_tf32(dcol, dAh, dBl, idesc, 1u);
+                            tc::mma_tf32(dcol, dAh, dBh, idesc, 1u);
+                        }
+                    }
+                    tc::mma_commit(tc_bar);
+                }
+                if (it + PD < nitem) fetch(it + PD, pa[sl], pb[sl], false);
+                if (it + PD + kTcL2Ahead < nitem) fetch(it + PD + kTcL2Ahead, pa[sl], pb[sl], true);
+            }
+        }
+    }
+    // ---- W[r, j0 + c] -= acc: warp -> (tile, TMEM lane quarter, 32-column half); the first half's W values are loaded while the
+    // last MMAs run (one half at a time: 32 + 32 registers)
+    const int warp = tid >> 5, lane = tid & 31;
+    const int tile = (warp >> 2) & 1, qd = warp & 3, ch = warp >> 3;
+    const int rl = tile * 128 + qd * 32 + lane;
+    float4 wv[8];
+    auto load_w = [&](int h) {
+        if (h * kTcRows + rl < rows) {
+            const float* w = W + (size_t)(r0 + h * kTcRows + rl) * ldw + j0 + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wv[j] = *reinterpret_cast<const float4*>(w + 4 * j);
+        }
+    };
+    load_w(0);
+    tc::mbar_wait(tc_bar, phase); phase ^= 1u;
+    tc::fence_after();
+    for (int h = 0; h < nh; ++h) {
+        if (h > 0) load_w(h);
+        if (tile < tiles_of(h)) {                                               // (uniform across the warp)
+            uint32_t v[32];
+            tc::tmem_ld32(tmem + (uint32_t)((h * 2 + tile) * kNB + ch * 32) + ((uint32_t)(qd * 32) << 16), v);
+            if (h * kTcRows + rl < rows) {
+                float* w = W + (size_t)(r0 + h * kTcRows + rl) * ldw + j0 + ch * 32;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 x = wv[j];
+                    x.x -= __uint_as_float(v[4 * j]); x.y -= __uint_as_float(v[4 * j + 1]);
+                    x.z -= __uint_as_float(v[4 * j + 2]); x.w -= __uint_as_float(v[4 * j + 3]);
+                    *reinterpret_cast<float4*>(w + 4 * j) = x;
+                }
+            }
+        }
+    }
+    tc::fence_before();
+    __syncthreads();
+    if (tid == 0) tc_phase_s = phase;               // (read again after the barriers of the diagonal block / row solves)
+}
+
 // Blocked left-looking Cholesky of the nf x nf lower triangle in W (row stride ldw): W <- L.
+template <bool TC>
 __device__ void chol_blocked(float* __restrict__ W, int ldw, int nf, float floor_, const DenseSmem& S, int tid) {
     constexpr int LD = kNB + 1;
     CPROF_BEGIN();
@@ -229,7 +383,10 @@ __device__ void chol_blocked(float* __restrict__ W, int ldw, int nf, float floor
         for (int r0 = j0; r0 < nf;) {
             const int rem = nf - r0;
             const int rows = rem > 256 ? 512 : (rem > 128 ? 256 : (rem > 64 ? 128 : 64));      // rows of this chunk
-            if (j0 > 0) {
+            if constexpr (TC) {
+                if (j0 > 0)
+                    chol_update_tc(W, ldw, nf, j0, r0, rows < nf - r0 ? rows : nf - r0, S.As, tid);
+            } else if (j0 > 0) {
                 if (rows == 512) chol_update_chunk<8>(W, ldw, nf, j0, r0, S, tid);
                 else if (rows == 256) chol_update_chunk<4>(W, ldw, nf, j0, r0, S, tid);
                 else if (rows == 128) chol_update_chunk<2>(W, ldw, nf, j0, r0, S, tid);
@@ -486,7 +643,9 @@ __device__ double kkt_residual(const double* lam, const double* g, int m, Ctx& c
 enum { DP_SETUP = 0, DP_KKT = 1, DP_FREESET = 2, DP_GATHER = 3, DP_CHOL = 4, DP_TRISOLVE = 5, DP_LS_GRAM = 6, DP_LS_TRUE = 7,
        DP_TRUEGRAD = 8, DP_EPILOGUE = 9, DP_SWITCH = 10, DP_NFACT = 11, DP_NITER = 12 };
 
-template <class TIO>
+// TC: the Cholesky block-column update runs on the tensor cores (a separate instantiation, so that the register allocation of
+// each variant only sees the update it uses).
+template <class TIO, bool TC>
 __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
     extern __shared__ __align__(16) char dsm[];
     __shared__ double red[64];
@@ -513,7 +672,8 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
         S.fl = (int*)o; o += (size_t)mp * 4; S.flp = (int*)o; o += (size_t)mp * 4;
         S.arow = (int*)o; o += (size_t)mp * 4; S.sup = (int*)o; o += (size_t)mp * 4;
         S.xs = (float*)o; o += (size_t)mp * 4;
-        S.As = (float*)o; o += (size_t)kKS * kRC * 4; S.Bs = (float*)o; o += (size_t)kKS * kNB * 4;
+        S.As = (float*)o; S.Bs = S.As + (size_t)kKS * kRC;
+        o += TC ? (size_t)kTcBytes + 1024 : (size_t)kStageSimt;    // (TC: the 1024-byte aligned operand planes lie over As / Bs)
         S.Dt = (float*)o; o += (size_t)kNB * kNB * 4;
         S.D = (float*)o; o += (size_t)kNB * (kNB + 1) * 4; S.invd = (float*)o;
 #ifdef CAVE_DENSE_PROFILE
@@ -521,6 +681,21 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
 #else
         S.prof = nullptr;
 #endif
+    }
+    if constexpr (TC) {
+        // TMEM: 256 columns = four 128 x 64 float32 accumulator tiles of the Cholesky update (one CTA per SM: no contention)
+        if (tid == 0) {
+            tc::mbar_init(&tc_bar_s, 1);
+            tc_phase_s = 0;
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (tid < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tc::smem_u32(&tmem_base_s)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        tc::fence_before();
+        __syncthreads();
+        tc::fence_after();
     }
     const TIO* pred_all = (const TIO*)p.pred;
     TIO* grad_all = (TIO*)p.grad;
@@ -664,7 +839,7 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
                         for (int a = tid; a < nf; a += kDT) S.flp[a] = S.fl[a];
                         __syncthreads();
                         DPROF(DP_GATHER);
-                        chol_blocked(W, mp, nf, floorf_, S, tid);
+                        chol_blocked<TC>(W, mp, nf, floorf_, S, tid);
                         nf_fact = nf;
                         DPROF(DP_CHOL);
 #ifdef CAVE_DENSE_PROFILE
@@ -754,19 +929,39 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
         __syncthreads();
         DPROF(DP_EPILOGUE);
     }
+    if constexpr (TC) {
+        tc::fence_before();
+        __syncthreads();
+        if (tid < 32) {
+            tc::fence_after();
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base_s) : "memory");
+        }
+    }
 }
 
-cudaError_t launch_dense_solve(const DenseParams& p, cudaStream_t stream) {
-    const size_t smem = dense_solve_smem(p.L.m_pad);
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = p.io_f32 ? cudaFuncSetAttribute(dense_solve_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                             : cudaFuncSetAttribute(dense_solve_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t launch_dense_solve(const DenseParams& p_in, cudaStream_t stream) {
+    DenseParams p = p_in;
+    // static shared memory of the kernel (reduction scratch, counters, mbarrier): 1.6 KB
+    const size_t budget = 227 * 1024 - 2048;
+    // Opt-in (CAVE_DENSE_TC=1).  Measured on B200 at 1225 x 1024: the update itself drops from 3.44 to 1.62 Mclk per instance, but
+    // in the instantiation that contains it ptxas splits the 32-deep load batches of the residual / matvec / triangular-solve
+    // loops (128-register cap), which costs the other phases what the update gains: 18.4 k inst/s either way.
+    const char* e_tc = getenv("CAVE_DENSE_TC");
+    p.tc_update = e_tc && atoi(e_tc) != 0 && dense_solve_smem(p.L.m_pad, true) <= budget ? 1 : 0;
+    size_t smem = dense_solve_smem(p.L.m_pad, p.tc_update != 0);
+    if (smem > budget) return cudaErrorInvalidValue;
+    if (const char* e_pad = getenv("CAVE_DENSE_SMEM_PAD")) {  // diagnostics: unused extra shared memory (moves the L1 / shared-memory split)
+        const size_t want = smem + (size_t)atoi(e_pad);
+        smem = want < budget ? want : budget;
+    }
+    void (*kern)(DenseParams) = p.tc_update ? (p.io_f32 ? dense_solve_kernel<float, true> : dense_solve_kernel<double, true>)
+                                            : (p.io_f32 ? dense_solve_kernel<float, false> : dense_solve_kernel<double, false>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)(p.L.n_slots < sms ? p.L.n_slots : sms);
-    if (p.io_f32) dense_solve_kernel<float><<<grid, kDT, smem, stream>>>(p);
-    else dense_solve_kernel<double><<<grid, kDT, smem, stream>>>(p);
+    kern<<<grid, kDT, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -66,6 +66,8 @@ class _CaveCudaFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         (grad,) = ctx.saved_tensors
+        if not ctx.per_instance and grad.device.type == "cpu" and grad_out.device.type == "cpu" and float(grad_out) == 1.0:
+            return grad, None, None, None, None, None, None       # loss.backward() on host tensors: no 4 B d host multiply
         g = grad_out.unsqueeze(1) * grad if ctx.per_instance else grad_out * grad
         return g.to(grad.dtype), None, None, None, None, None, None
 

@@ -109,3 +109,25 @@ def test_dense_batch_in_several_rounds_and_mixed_with_structured_instances():
     scale = float(one["proj"][ok].abs().max())
     assert float((out["proj"][ok] - one["proj"][ok]).abs().max()) <= 1e-8 * scale
     assert float((out["loss_i"][ok] - one["loss_i"][ok]).abs().max()) <= 1e-9
+
+
+@pytest.mark.parametrize("d,m,B", [(1225, 1024, 3), (640, 512, 4), (333, 300, 5)])
+def test_tensor_core_cholesky_update_matches_ffma_update_and_oracle(d, m, B, monkeypatch):
+    """CAVE_DENSE_TC=1 runs the block-column update of the dense Cholesky on the tensor cores (tcgen05, 3 x TF32, accumulators
+    in TMEM) instead of the FFMA micro-kernel.  The factor only preconditions the Newton steps (the polish phase works on A in
+    float64), so both variants must reach the same projection, and the oracle's."""
+    from cave_b200 import _lib, cave_forward_backward
+    A, c = _dense(B, m, d, seed=d * 3 + m)
+    A[B - 1, m - 37:] = 0                                   # ragged: 37 padding rows (block column with < 64 rows)
+    monkeypatch.setenv("CAVE_DENSE_TC", "0")
+    ref = cave_forward_backward(c, A, 1.0, 0, reduction="none", want_proj=True, want_status=True, dense=True)
+    monkeypatch.setenv("CAVE_DENSE_TC", "1")
+    out = cave_forward_backward(c, A, 1.0, 0, reduction="none", want_proj=True, want_status=True, dense=True)
+    st = out["status"].cpu().numpy()
+    assert ((st & _lib.ST_PATH_GRAM) != 0).all() and ((st & 0xff) == 0).all(), st
+    scale = float(ref["proj"].abs().max())
+    assert float((out["proj"] - ref["proj"]).abs().max()) <= 1e-8 * scale
+    assert float((out["grad"] - ref["grad"]).abs().max()) <= 1e-8 * max(float(ref["grad"].abs().max()), 1e-30)
+    ref_p, ref_r = O.batch_project(c[:2].cpu().numpy(), A[:2].cpu().numpy(), fp64=True)
+    assert np.abs(out["proj"][:2].cpu().numpy() - ref_p).max() <= 1e-5 * np.abs(ref_p).max()
+    np.testing.assert_allclose(out["rnorm"][:2].cpu().numpy(), ref_r, rtol=1e-7, atol=1e-9)

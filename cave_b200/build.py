@@ -18,6 +18,12 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 
+# dense_solve.cu is compiled as relocatable device code: its heavy phases are non-inlined functions, and only with the strict
+# call ABI of -rdc does ptxas give every callee the full register budget (saving the caller's live registers at the call);
+# without it the callees are cloned per kernel and squeezed into what the call site leaves free, which splits their load batches.
+PER_FILE_FLAGS = {"dense_solve.cu": ["-rdc=true", "-maxrregcount=128"]}     # (512-thread kernel: 128 registers per thread, callees included)
+
+
 def _nvcc() -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
@@ -42,7 +48,8 @@ def build(force: bool = False, verbose: bool = False, alt_name: str | None = Non
     procs = []
     for s in SOURCES:
         obj = os.path.join(OUT_DIR, s.replace(".cu", ".o") if alt_name is None else s.replace(".cu", ".alt.o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("CAVE_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, s), "-o", obj]
+        cmd = [_nvcc(), *NVCC_FLAGS, *PER_FILE_FLAGS.get(s, []), *os.environ.get("CAVE_NVCC_EXTRA", "").split(),
+               "-c", os.path.join(CSRC, s), "-o", obj]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for s, pr in procs:

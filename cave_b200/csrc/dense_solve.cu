@@ -49,6 +49,9 @@ struct DenseSmem {
 #ifndef CAVE_TC_INLINE
 #define CAVE_TC_INLINE __noinline__
 #endif
+#ifndef CAVE_TC_KMAJOR
+#define CAVE_TC_KMAJOR 0
+#endif
 #ifndef CAVE_TC_PD
 #define CAVE_TC_PD 1
 #endif
@@ -317,6 +320,20 @@ __device__ CAVE_TC_INLINE void chol_update_tc(float* __restrict__ W, int ldw, in
                 if (tid == 0) {
                     tc::fence_after();
                     const uint32_t aH = tc::smem_u32(Ah), aL = tc::smem_u32(Al), bH = tc::smem_u32(Bh), bL = tc::smem_u32(Bl);
+#if CAVE_TC_KMAJOR
+                    // k-step outermost: consecutive instructions alternate between the two tiles' accumulators
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t dBh = tc::smem_desc(bH + kk * 32), dBl = tc::smem_desc(bL + kk * 32);
+                        for (int t = 0; t < nt; ++t) {
+                            const uint32_t dcol = tmem + (uint32_t)(h * 2 + t) * kNB;
+                            const uint64_t dAh = tc::smem_desc(aH + t * 16384 + kk * 32), dAl = tc::smem_desc(aL + t * 16384 + kk * 32);
+                            tc::mma_tf32(dcol, dAl, dBh, idesc, (s | kk) != 0 ? 1u : 0u);
+                            tc::mma_tf32(dcol, dAh, dBl, idesc, 1u);
+                            tc::mma_tf32(dcol, dAh, dBh, idesc, 1u);
+                        }
+                    }
+#else
                     for (int t = 0; t < nt; ++t) {
                         const uint32_t dcol = tmem + (uint32_t)(h * 2 + t) * kNB;
 #pragma unroll
@@ -328,6 +345,7 @@ __device__ CAVE_TC_INLINE void chol_update_tc(float* __restrict__ W, int ldw, in
                             tc::mma_tf32(dcol, dAh, dBh, idesc, 1u);
                         }
                     }
+#endif
                     tc::mma_commit(tc_bar);
                 }
                 if (it + PD < nitem) fetch(it + PD, pa[sl], pb[sl], false);
@@ -632,6 +650,56 @@ __device__ double kkt_residual(const double* lam, const double* g, int m, Ctx& c
     return cx.block_max(res);
 }
 
+// ---- Outlined shells (by-value arguments only, so nothing of the caller lives in memory): each heavy phase gets a register
+// allocation of its own.  Inside the 128-register kernel ptxas sized the load batches of these loops by whatever else was
+// live at the call site (e.g. the 32 loads in flight of true_residual came out as 10 + 9 + 8 in one instantiation and the
+// phase ran three times slower), which made every phase depend on unrelated code.
+#ifndef OUT_RES
+#define OUT_RES 1
+#endif
+#ifndef OUT_GRAD
+#define OUT_GRAD 1
+#endif
+#ifndef OUT_MV
+#define OUT_MV 1
+#endif
+#ifndef OUT_TRI
+#define OUT_TRI 0
+#endif
+#ifndef OUT_CHOL
+#define OUT_CHOL 0
+#endif
+struct Pair64 { double a, b; };
+template <class TIO>
+__device__ __noinline__ double true_residual_o(const float* Ainst, int d, int m, const double* x, const TIO* c, double* rout, int* sup,
+                                               int* arow, double* red, int* s_cnt) {
+    DenseSmem S; S.sup = sup; S.arow = arow;
+    Ctx cx(red);
+    return true_residual<TIO>(Ainst, d, m, x, c, rout, S, cx, s_cnt);
+}
+__device__ __noinline__ void true_gradient_o(const float* Ainst, int d, int m, const double* r, double* g, int* arow, double* red) {
+    DenseSmem S; S.arow = arow;
+    Ctx cx(red);
+    true_gradient(Ainst, d, m, r, g, S, cx);
+}
+__device__ __noinline__ Pair64 gram_matvec_o(const float* G, int ldg, int m, const double* lamt, const double* lamp, const double* bb,
+                                             double* gt, double* red) {
+    Ctx cx(red);
+    Pair64 r;
+    gram_matvec(G, ldg, m, lamt, lamp, bb, gt, cx, r.a, r.b);
+    return r;
+}
+__device__ __noinline__ void chol_solve_o(const float* W, int ldw, int nf, float* As, float* D, float* invd, float* xs, int tid) {
+    DenseSmem S; S.As = As; S.D = D; S.invd = invd; S.xs = xs;
+    chol_solve_blocked(W, ldw, nf, S, tid);
+}
+template <bool TC>
+__device__ __noinline__ void chol_blocked_o(float* W, int ldw, int nf, float floor_, float* As, float* Bs, float* D, float* Dt, float* invd,
+                                            unsigned long long* prof, int tid) {
+    DenseSmem S; S.As = As; S.Bs = Bs; S.D = D; S.Dt = Dt; S.invd = invd; S.prof = prof;
+    chol_blocked<TC>(W, ldw, nf, floor_, S, tid);
+}
+
 // Coarse phase clocks (thread 0, clock64 deltas summed over instances): only in -DCAVE_DENSE_PROFILE builds.
 #ifdef CAVE_DENSE_PROFILE
 #define DPROF_BEGIN() long long dprof_t = clock64()
@@ -780,8 +848,9 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
                     if (res > 1e-4 * scale) { handed_back = true; why = 1; why_phase = 1; break; }       // the Gram-space iteration did not settle
                     // ---- switch to the true problem: r = c - A^T lam, g = -A r
                     phase = 2; since_best = 0; res_best = 1e300;
-                    f = 0.5 * true_residual<TIO>(Ainst, d, m, lam, c, rc, S, cx, &s_cnt);
-                    true_gradient(Ainst, d, m, rc, g, S, cx);
+                    f = 0.5 * (OUT_RES ? true_residual_o<TIO>(Ainst, d, m, lam, c, rc, S.sup, S.arow, red, &s_cnt)
+                                                  : true_residual<TIO>(Ainst, d, m, lam, c, rc, S, cx, &s_cnt));
+                    if (OUT_GRAD) true_gradient_o(Ainst, d, m, rc, g, S.arow, red); else true_gradient(Ainst, d, m, rc, g, S, cx);
                     res = kkt_residual(lam, g, m, cx);
                     DPROF(DP_SWITCH);
                 }
@@ -839,7 +908,8 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
                         for (int a = tid; a < nf; a += kDT) S.flp[a] = S.fl[a];
                         __syncthreads();
                         DPROF(DP_GATHER);
-                        chol_blocked<TC>(W, mp, nf, floorf_, S, tid);
+                        if (OUT_CHOL) chol_blocked_o<TC>(W, mp, nf, floorf_, S.As, S.Bs, S.D, S.Dt, S.invd, S.prof, tid);
+                        else chol_blocked<TC>(W, mp, nf, floorf_, S, tid);
                         nf_fact = nf;
                         DPROF(DP_CHOL);
 #ifdef CAVE_DENSE_PROFILE
@@ -848,7 +918,7 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
                     }
                     for (int a = tid; a < nf; a += kDT) S.xs[a] = (float)g[S.fl[a]];
                     __syncthreads();
-                    chol_solve_blocked(W, mp, nf, S, tid);
+                    if (OUT_TRI) chol_solve_o(W, mp, nf, S.As, S.D, S.invd, S.xs, tid); else chol_solve_blocked(W, mp, nf, S, tid);
                     for (int a = tid; a < nf; a += kDT) S.dir[S.fl[a]] = (double)S.xs[a];
                 }
                 __syncthreads();
@@ -870,11 +940,13 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
                     dec = cx.block_sum(dec);
                     if (phase == 1) {
                         double lg, lb;
-                        gram_matvec(G, mp, m, lamt, S.lamp, S.bb, gt, cx, lg, lb);
+                        if (OUT_MV) { const Pair64 pr = gram_matvec_o(G, mp, m, lamt, S.lamp, S.bb, gt, red); lg = pr.a; lb = pr.b; }
+                        else gram_matvec(G, mp, m, lamt, S.lamp, S.bb, gt, cx, lg, lb);
                         ft = 0.5 * lg - 0.5 * lb;
                         DPROF(DP_LS_GRAM);
                     } else {
-                        ft = 0.5 * true_residual<TIO>(Ainst, d, m, lamt, c, rtr, S, cx, &s_cnt);
+                        ft = 0.5 * (OUT_RES ? true_residual_o<TIO>(Ainst, d, m, lamt, c, rtr, S.sup, S.arow, red, &s_cnt)
+                                                       : true_residual<TIO>(Ainst, d, m, lamt, c, rtr, S, cx, &s_cnt));
                         DPROF(DP_LS_TRUE);
                     }
                     const double fa = fabs(f);
@@ -899,7 +971,7 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
                 if (phase == 1) { double* t2 = g; g = gt; gt = t2; }
                 else {
                     { double* t3 = rc; rc = rtr; rtr = t3; }
-                    true_gradient(Ainst, d, m, rc, g, S, cx);
+                    if (OUT_GRAD) true_gradient_o(Ainst, d, m, rc, g, S.arow, red); else true_gradient(Ainst, d, m, rc, g, S, cx);
                     DPROF(DP_TRUEGRAD);
                     if (at_floor) { status = ST_CONVERGED; break; }
                 }
@@ -943,11 +1015,12 @@ cudaError_t launch_dense_solve(const DenseParams& p_in, cudaStream_t stream) {
     DenseParams p = p_in;
     // static shared memory of the kernel (reduction scratch, counters, mbarrier): 1.6 KB
     const size_t budget = 227 * 1024 - 2048;
-    // Opt-in (CAVE_DENSE_TC=1).  Measured on B200 at 1225 x 1024: the update itself drops from 3.44 to 1.62 Mclk per instance, but
-    // in the instantiation that contains it ptxas splits the 32-deep load batches of the residual / matvec / triangular-solve
-    // loops (128-register cap), which costs the other phases what the update gains: 18.4 k inst/s either way.
+    // Default when its operand planes fit beside the solver's vectors (m_pad <= 1408); CAVE_DENSE_TC=0 keeps the FFMA update.
+    // Measured on B200 at 1225 x 1024: update 3.5 -> 1.8 Mclk per instance, 18.5 k -> 20.0 k inst/s.  (It only pays with the
+    // outlined phases + -rdc: inlined into the 128-register kernel, ptxas sized the load batches of the residual / matvec /
+    // triangular-solve loops by what the call site left free and the other phases lost what the update gained: DESIGN.md 4.3.)
     const char* e_tc = getenv("CAVE_DENSE_TC");
-    p.tc_update = e_tc && atoi(e_tc) != 0 && dense_solve_smem(p.L.m_pad, true) <= budget ? 1 : 0;
+    p.tc_update = (!e_tc || atoi(e_tc) != 0) && dense_solve_smem(p.L.m_pad, true) <= budget ? 1 : 0;
     size_t smem = dense_solve_smem(p.L.m_pad, p.tc_update != 0);
     if (smem > budget) return cudaErrorInvalidValue;
     if (const char* e_pad = getenv("CAVE_DENSE_SMEM_PAD")) {  // diagnostics: unused extra shared memory (moves the L1 / shared-memory split)

@@ -212,7 +212,7 @@ int cave_scratch_bytes(int64_t B, int64_t m_max, int64_t d, int compute_dtype, c
 
 struct SparseIn { const long long* inst_off; const long long* row_ptr; const int* col; const float* val; };
 static int pack_impl(const float* A, const int32_t* m_rows, int64_t B, int64_t m_max, int64_t d, void* pack, size_t pack_bytes,
-                     void* stream, bool emit_setup, const SparseIn* sparse = nullptr) {
+                     void* stream, bool emit_setup, const SparseIn* sparse = nullptr, bool skip_avg = false) {
     if ((!A && !sparse) || !pack) return fail(CAVE_EINVAL, "A and pack must not be null");
     if (int e = check_shape(B, m_max, d)) return e;
     const cave::PackLayout L = cave::make_pack_layout(B, m_max, d);
@@ -227,7 +227,10 @@ static int pack_impl(const float* A, const int32_t* m_rows, int64_t B, int64_t m
     p.gen4 = (int4*)(base + L.gen); p.ctype = (unsigned char*)(base + L.ctype); p.avg = (float*)(base + L.avg);
     p.ghash = (ulonglong2*)(base + L.ghash); p.csr_col = (uint16_t*)(base + L.csr_col); p.csr_val = (float*)(base + L.csr_val);
     p.cap_nnz = (int)L.cap_nnz; p.csr_ok = (int*)(base + L.csrok); p.maxl1 = (float*)(base + L.maxl1); p.maxl2 = (float*)(base + L.maxl2);
+    p.skip_avg = skip_avg ? 1 : 0;
     cudaError_t e = cudaMemsetAsync(base + L.plan, 0, 64, (cudaStream_t)stream);
+    // marked in the pack: a later warm call in another mode reports CAVE_ST_BADINPUT instead of pushing towards a zero average
+    if (e == cudaSuccess && skip_avg) e = cudaMemsetAsync(base + L.plan + 8 * cave::PLAN_NO_AVG, 1, 1, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(CAVE_ECUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
     e = sparse ? cave::launch_scan_sparse(p, sparse->inst_off, sparse->row_ptr, sparse->col, sparse->val, (cudaStream_t)stream)
                : cave::launch_scan(p, (cudaStream_t)stream);
@@ -309,7 +312,9 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
 
     cudaStream_t st = (cudaStream_t)stream;
     if (!(opts && opts->warm_pack)) {
-        if (int e = pack_impl(A, m_rows, B, m_max, d, pack, pack_bytes, stream, env_int("CAVE_COLD_SETUP", 0) != 0)) return e;
+        // one-shot pack: the exact loss never reads the average of the normalised rows
+        if (int e = pack_impl(A, m_rows, B, m_max, d, pack, pack_bytes, stream, env_int("CAVE_COLD_SETUP", 0) != 0, nullptr,
+                              mode == CAVE_MODE_EXACT)) return e;
     }
     char* pb = (char*)pack;
     char* sb = (char*)scratch;
@@ -350,7 +355,7 @@ int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pre
         dp.A = A; dp.pred = pred; dp.B = (int)B; dp.m_max = (int)m_max; dp.d = (int)d;
         dp.inst_index = sp.inst_index; dp.n_packed = Bpack; dp.nvalid = sp.nvalid; dp.ngen = sp.ngen; dp.nsingc = sp.nsingc; dp.gen = sp.gen;
         dp.ctype = sp.ctype; dp.avg = sp.avg; dp.dpad = PL.dpad;
-        dp.ws = sb; dp.L = DL; dp.force = (opts && opts->dense_mode > 0) ? 1 : 0; dp.no_handback = env_int("CAVE_DENSE_NO_HANDBACK", 0); dp.trace_b = env_int("CAVE_DENSE_TRACE", -1);
+        dp.plan = (const unsigned long long*)(pb + PL.plan); dp.ws = sb; dp.L = DL; dp.force = (opts && opts->dense_mode > 0) ? 1 : 0; dp.no_handback = env_int("CAVE_DENSE_NO_HANDBACK", 0); dp.trace_b = env_int("CAVE_DENSE_TRACE", -1);
         dp.grad = grad; dp.proj = proj; dp.loss64 = sp.loss64; dp.rnorm64 = sp.rnorm64; dp.status = sp.status; dp.iters = sp.iters;
         dp.mode = mode; dp.inner_ratio = inner_ratio; dp.sign = sign; dp.gscale = sp.gscale;
         dp.max_iter = 0; dp.max_ls = sp.max_ls; dp.tol = sp.tol; dp.io_f32 = io_dtype == CAVE_F32; dp.nk = (int)(DL.d_pad / 32);

@@ -81,6 +81,7 @@ struct DenseParams {
     const unsigned char* ctype; // [*, dpad]
     const float* avg;           // [*, dpad]
     int64_t dpad;               // padded d of the pack (ctype / avg stride)
+    const unsigned long long* plan;   // the pack's plan block (PLAN_NO_AVG), nullable
     // workspace
     char* ws;                   // scratch base
     DenseLayout L;

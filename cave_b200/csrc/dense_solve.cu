@@ -835,7 +835,7 @@ __global__ void __launch_bounds__(kDT, 1) dense_solve_kernel(DenseParams p) {
         // when a line search has to cut the step to the order of 1 / G_vv (the signature of the identity scaling overshooting).
         bool scaled = osum * 0.25 < 0.25 * dsum;
         const double cnorm = sqrt(cc);
-        const bool finite_in = cc < 1e300;
+        const bool finite_in = cc < 1e300 && !(p.mode != MODE_EXACT && p.plan && p.plan[PLAN_NO_AVG] != 0ull);   // (or a pack without the average in a mode that needs it)
         DPROF(DP_SETUP);
         int status = ST_BADINPUT, iters = 0;
         bool handed_back = false;

@@ -104,7 +104,8 @@ CAVE_HD PackLayout make_pack_layout(int64_t B, int64_t m_max, int64_t d) {
 // Which one applies depends on the data (general rows, +- pairs, non-zeros), which only the device knows
 // after the scan; the plan kernel therefore reduces per-instance shared-memory footprints into PlanStats and
 // every candidate configuration is launched — the ones the statistics do not select exit at once.
-enum { PLAN_N = 0, PLAN_SUM8 = 1, PLAN_SUM4 = 2, PLAN_MAXHOT8 = 3, PLAN_MAXHOT4 = 4 };   // indices into plan[]
+enum { PLAN_N = 0, PLAN_SUM8 = 1, PLAN_SUM4 = 2, PLAN_MAXHOT8 = 3, PLAN_MAXHOT4 = 4,   // indices into plan[]
+       PLAN_NO_AVG = 7 };   // != 0: the pack was written without the average unit normal (one-shot pack of an exact-mode call)
 constexpr int kOrderMaxBatch = 16384;     // beyond this the drain is negligible and instances are taken in index order
 struct SolveConfig { int threads, ctas_per_sm, smem_bytes; };
 constexpr int kNumSolveConfigs = 4;

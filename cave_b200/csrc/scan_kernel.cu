@@ -444,12 +444,15 @@ __global__ void __launch_bounds__(NT) scan_rows_kernel(ScanParams p) {
             uint64_t hp = 0, hn = 0;
             const float* row = base + shift;
             int w = off;
-            for (int k0 = 0; k0 < d; k0 += 32) {
+            const bool want_avg = av && !p.skip_avg;
+            // (a dense row that does not fit the packed CSR of a call that needs no average has nothing left to do here:
+            // 1.25 M shared 64-bit atomics per 1024 x 1225 instance otherwise)
+            for (int k0 = 0; k0 < ((want_avg || fits) ? d : 0); k0 += 32) {
                 const int k = k0 + lane;
                 const float v = k < d ? row[k] : 0.f;
                 const unsigned nzm = __ballot_sync(0xffffffffu, v != 0.f);
                 if (v != 0.f) {
-                    if (av) atomicAdd(&avg_fx[k], (unsigned long long)__double2ll_rn((double)v * (double)inv * 1099511627776.0));
+                    if (want_avg) atomicAdd(&avg_fx[k], (unsigned long long)__double2ll_rn((double)v * (double)inv * 1099511627776.0));
                     if (fits) {
                         const int pos = w + __popc(nzm & ((1u << lane) - 1u));
                         col_out[pos] = (uint16_t)k; val_out[pos] = v;

@@ -22,6 +22,8 @@ struct ScanParams {
     int cap_nnz;
     int* csr_ok;            // 1 if every general row of the instance fitted into the packed CSR
     float *maxl1, *maxl2;   // max_i ||a_i||_1 and max_i ||a_i||_2^2 over the general rows
+    int skip_avg;           // 1: the average of the normalised rows is not needed (one-shot pack of an exact-mode call: the
+                            // exact loss has no push-inside step, src/cave.py:84-129); avg is then written as the singleton part only
 };
 
 cudaError_t launch_scan(const ScanParams& p, cudaStream_t stream);

@@ -35,8 +35,9 @@ __global__ void __launch_bounds__(CAVE_LB_T, CAVE_LB_C) solve_kernel(SolveParams
         const int b = p.order ? p.order[slot_b] : slot_b;
         if (p.dense_flag && p.dense_flag[b]) continue;                            // solved by the dense (Gram) path
         const long long qi = p.inst_index ? (long long)p.inst_index[b] : (long long)b;
-        if (qi < 0 || qi >= p.n_packed) {
-            // an index outside the pack (stale permutation, another shard's index): report, never read out of bounds
+        if (qi < 0 || qi >= p.n_packed || (p.mode != MODE_EXACT && p.plan[PLAN_NO_AVG] != 0ull)) {
+            // an index outside the pack (stale permutation, another shard's index): report, never read out of bounds;
+            // likewise a pack without the average unit normal used by a mode that pushes towards it
             if (cx.tid == 0) { p.loss64[b] = NAN; p.rnorm64[b] = NAN; p.status[b] = ST_BADINPUT; p.iters[b] = 0; }
             for (int k = cx.tid; k < p.d; k += cx.nthr) { grad[(size_t)b * p.d + k] = (TIO)NAN; if (proj) proj[(size_t)b * p.d + k] = (TIO)NAN; }
             continue;

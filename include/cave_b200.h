@@ -160,7 +160,9 @@ int cave_pack_sparse(const int64_t* inst_off, const int64_t* row_ptr, const int3
  *   proj    [B,d] projection of c = sign*pred onto the cone  (what _batch_project returns)
  *   rnorm   [B]   ||proj - c||_2                               (nnls meaning, src/cave.py:307)
  *   status  [B]   int32 CAVE_ST_*;   iters [B] int32 solver iterations
- * Unless opts->warm_pack is set, cave_pack() is run first on the same stream. */
+ * Unless opts->warm_pack is set, cave_pack() is run first on the same stream — in CAVE_MODE_EXACT without the average
+ * unit normal, which that mode never reads (the pack is marked: a later warm call with it in another mode reports
+ * CAVE_ST_BADINPUT for every instance; build packs that are shared between modes with cave_pack()). */
 int cave_forward_backward(const float* A, const int32_t* m_rows, const void* pred,
                           int64_t B, int64_t m_max, int64_t d,
                           double sign, int mode, double inner_ratio, int reduction,

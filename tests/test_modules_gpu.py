@@ -284,3 +284,50 @@ def test_no_write_outside_the_callers_buffers():
     A = torch.randn((5, 200, 260), generator=g, device=dev); A[3, 190:] = 0; c = torch.randn((5, 260), generator=g, device=dev)
     st = run(A, c, 0, _lib.SolverOpts(0, 0, 0.0, 0, 0, 0, 1, None, 0, 2))            # dense path, slots = 2 -> three rounds
     assert ((st & _lib.ST_PATH_GRAM) != 0).all() and ((st & 0xff) == 0).all()
+
+
+def test_one_shot_exact_pack_has_no_average_and_is_refused_by_the_other_modes():
+    """A cold cave_forward_backward in CAVE_MODE_EXACT packs without the average unit normal (the exact loss never reads it,
+    src/cave.py:84-129).  The pack is marked: reusing it (warm) for the exact mode is fine, for CaVE+ / heuristic every
+    instance reports CAVE_ST_BADINPUT with NaN outputs instead of being pushed towards a zero average."""
+    import ctypes
+    from cave_b200 import _lib, synth
+    from cave_b200.qpsolver import _opts, _ptr
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    insts = synth.make_batch("tsp20", 5, seed=11)
+    A = synth.densify(insts, device=dev)
+    pred = torch.tensor(synth.predictions(insts, 11, "near"), device=dev, dtype=torch.float32)
+    B, m, d = A.shape
+    nb = ctypes.c_size_t()
+    _lib.check(lib.cave_pack_bytes(B, m, d, ctypes.byref(nb)))
+    pack = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+
+    def call(mode, warm):
+        opts = _opts(warm=warm)
+        _lib.check(lib.cave_scratch_bytes(B, m, d, 1, ctypes.byref(opts), ctypes.byref(nb)))
+        scratch = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        loss_i = torch.empty(B, dtype=torch.float32, device=dev)
+        grad = torch.empty((B, d), dtype=torch.float32, device=dev)
+        rnorm = torch.empty(B, dtype=torch.float32, device=dev)
+        status = torch.empty(B, dtype=torch.int32, device=dev)
+        iters = torch.empty(B, dtype=torch.int32, device=dev)
+        _lib.check(lib.cave_forward_backward(
+            _ptr(A), None, _ptr(pred), B, m, d, -1.0, mode, 0.2, _lib.REDUCE["mean"], _lib.F32, 1, ctypes.byref(opts),
+            _ptr(loss), _ptr(loss_i), _ptr(grad), None, _ptr(rnorm), _ptr(status), _ptr(iters), _ptr(pack), pack.numel(),
+            _ptr(scratch), scratch.numel(), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        torch.cuda.synchronize()
+        return status.cpu().numpy() & 0xff, float(loss), grad
+
+    st_cold, loss_cold, grad_cold = call(_lib.MODE_EXACT, warm=False)
+    assert (st_cold == _lib.ST_CONVERGED).all()
+    st_warm, loss_warm, grad_warm = call(_lib.MODE_EXACT, warm=True)
+    assert (st_warm == _lib.ST_CONVERGED).all() and loss_warm == loss_cold and torch.equal(grad_warm, grad_cold)
+    st_inner, loss_inner, grad_inner = call(_lib.MODE_INNER, warm=True)
+    assert (st_inner == _lib.ST_BADINPUT).all() and np.isnan(loss_inner) and bool(torch.isnan(grad_inner).all())
+    # a cold call in the pushing mode writes the full pack again
+    st2, loss2, _ = call(_lib.MODE_INNER, warm=False)
+    assert (st2 == _lib.ST_CONVERGED).all() and np.isfinite(loss2)
+    st3, loss3, _ = call(_lib.MODE_INNER, warm=True)
+    assert (st3 == _lib.ST_CONVERGED).all() and loss3 == loss2

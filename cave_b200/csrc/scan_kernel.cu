@@ -300,7 +300,9 @@ __global__ void __launch_bounds__(NT) scan_kernel(ScanParams p) {
 // refills with TMA bulk copies, so eight independent row streams are in flight per CTA.  Cross-row
 // state is either warp-private (fixed order => reproducible) or exact under reordering (integer
 // atomics); the ordered general-row list is assembled once per instance after a single barrier.
-template <int NT, int S>
+// SKIPAVG: instantiation for packs that need no average (ScanParams::skip_avg); the default instantiation is textually the
+// round-1 kernel (a run-time test in the row loop changed its register allocation, 56 -> 48, and cost the TSP-50 scan 4 %).
+template <int NT, int S, bool SKIPAVG = false>
 __global__ void __launch_bounds__(NT) scan_rows_kernel(ScanParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -444,15 +446,14 @@ __global__ void __launch_bounds__(NT) scan_rows_kernel(ScanParams p) {
             uint64_t hp = 0, hn = 0;
             const float* row = base + shift;
             int w = off;
-            const bool want_avg = av && !p.skip_avg;
-            // (a dense row that does not fit the packed CSR of a call that needs no average has nothing left to do here:
-            // 1.25 M shared 64-bit atomics per 1024 x 1225 instance otherwise)
-            for (int k0 = 0; k0 < ((want_avg || fits) ? d : 0); k0 += 32) {
+            // (SKIPAVG: a row that does not fit the packed CSR has nothing left to do here: 1.25 M shared 64-bit atomics per
+            // 1024 x 1225 dense instance otherwise)
+            for (int k0 = 0; k0 < ((SKIPAVG && !fits) ? 0 : d); k0 += 32) {
                 const int k = k0 + lane;
                 const float v = k < d ? row[k] : 0.f;
                 const unsigned nzm = __ballot_sync(0xffffffffu, v != 0.f);
                 if (v != 0.f) {
-                    if (want_avg) atomicAdd(&avg_fx[k], (unsigned long long)__double2ll_rn((double)v * (double)inv * 1099511627776.0));
+                    if (av && !SKIPAVG) atomicAdd(&avg_fx[k], (unsigned long long)__double2ll_rn((double)v * (double)inv * 1099511627776.0));
                     if (fits) {
                         const int pos = w + __popc(nzm & ((1u << lane) - 1u));
                         col_out[pos] = (uint16_t)k; val_out[pos] = v;
@@ -578,14 +579,14 @@ cudaError_t launch_scan(const ScanParams& p0, cudaStream_t stream) {
             int dev = 0;
             if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
             size_t& conf = S == 2 ? configured2[dev] : configured3[dev];
-            if (smem > conf) {
-                cudaError_t e = S == 2 ? cudaFuncSetAttribute(scan_rows_kernel<NT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                       : cudaFuncSetAttribute(scan_rows_kernel<NT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            void (*kern)(ScanParams) = p.skip_avg ? (S == 2 ? scan_rows_kernel<NT, 2, true> : scan_rows_kernel<NT, 3, true>)
+                                                  : (S == 2 ? scan_rows_kernel<NT, 2> : scan_rows_kernel<NT, 3>);
+            if (smem > conf || p.skip_avg) {        // (the skip-average instantiations are rare: set their attribute every time)
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
-                conf = smem;
+                if (!p.skip_avg) conf = smem;
             }
-            if (S == 2) scan_rows_kernel<NT, 2><<<dim3((unsigned)p.B), dim3(NT), smem, stream>>>(p);
-            else scan_rows_kernel<NT, 3><<<dim3((unsigned)p.B), dim3(NT), smem, stream>>>(p);
+            kern<<<dim3((unsigned)p.B), dim3(NT), smem, stream>>>(p);
             return cudaGetLastError();
         }
     }

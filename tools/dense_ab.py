@@ -1,6 +1,7 @@
 """A/B timing of dense-path knobs inside ONE process (same box, same clocks): alternates environment settings that the
 library reads per launch (e.g. CAVE_DENSE_TC=1 / 0) and prints the median device time of each.
-usage: python tools/dense_ab.py d m B reps VAR=a,b [VAR2=c,d ...]   (settings are zipped, not crossed)"""
+usage: python tools/dense_ab.py d m B reps VAR=a,b [VAR2=c,d ...]   (settings are zipped, not crossed; DENSE_SLOTS=n is passed as
+dense_slots)"""
 import os, sys, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -21,7 +22,8 @@ for rep in range(reps + 1):
         for k, v in zip(names, s): os.environ[k] = v
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = cave_forward_backward(c, A, 1.0, 0, reduction="none", want_status=True, dense=True)
+        out = cave_forward_backward(c, A, 1.0, 0, reduction="none", want_status=True, dense=True,
+                                    dense_slots=int(os.environ.get("DENSE_SLOTS", "0")) or None)
         e1.record(); torch.cuda.synchronize()
         if rep: times[s].append(e0.elapsed_time(e1))
         if ref is None: ref = out["grad"].clone()

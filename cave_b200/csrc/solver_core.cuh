@@ -21,6 +21,9 @@
 // Nothing here is first order: no step-size/momentum pair that could reproduce the FISTA
 // divergence documented in the reference README (README.md:40).
 #pragma once
+#if defined(CAVE_NW_TRACE)
+#include <stdio.h>
+#endif
 #include "ctx.cuh"
 
 namespace cave {
@@ -879,10 +882,13 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<TC, HOT>
     const HPtr<T, HOT> rc = W.r;       // r is updated in place by every trial evaluation
     T f, dummy = (T)0;
     nw_eval2(cx, W, nu, rc, f, dummy);
-    int status = ST_ITER_CAP, it = 0, since_best = 0;
+    int status = ST_ITER_CAP, it = 0, since_best = 0, flat = 0;
     T res_best = (T)1e300;
     for (; it < max_iter; ++it) {
         const T res = nw_grad(cx, W, rc, W.g, nu);
+#if defined(CAVE_NW_TRACE) && !defined(CAVE_HOST_SIM)
+        if (cx.tid == 0 && it < 40) printf("it %d res %.6e tol %.3e f %.17g res_best %.3e since %d\n", it, (double)res, (double)tol, (double)f, (double)res_best, since_best);
+#endif
         if (!(res > tol)) { status = ST_CONVERGED; break; }
         // stagnation at the floating-point floor: the KKT residual is already tiny and has not halved for five
         // iterations (it hovers a hair above the tolerance) -> converged, not an iteration-cap failure
@@ -1033,6 +1039,9 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<TC, HOT>
             if (ft <= f - (T)1e-4 * dec + (T)4 * eps_mach<T>() * f) { ok = true; break; }
             alpha *= (T)0.5;
         }
+#if defined(CAVE_NW_TRACE) && !defined(CAVE_HOST_SIM)
+        if (cx.tid == 0 && it < 40) printf("   nf %d alpha %.3e ft %.17g ok %d floor %d\n", nf, (double)alpha, (double)ft, (int)ok, (int)at_floor);
+#endif
         if (!ok) {                    // r holds the last rejected trial: restore it for the current iterate
             T d0 = (T)0;
             nw_eval2(cx, W, nu, rc, f, d0);
@@ -1040,8 +1049,15 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<TC, HOT>
             break;
         }
         HPtr<T, HOT> t1 = nu; nu = nut; nut = t1;
+        // Accepted steps that no longer decrease f by a representable amount (the Armijo slack lets a step of length ~2^-24
+        // through after two dozen halvings): the iterate sits at the floating-point floor of a degenerate instance with the
+        // KKT residual a few tens of tol above the tolerance.  Three in a row end the solve instead of running to the
+        // iteration cap (SP 5x5, seed 1001 #3905: 200 iterations x 25 evaluations = 5 ms for one 90 x 40 instance).
+        // (only steps that were cut below 2^-10: a full step along a degenerate pivot may leave f unchanged and still move on)
+        flat = (alpha > (T)0.0009765625 || ft < f - (T)16 * eps_mach<T>() * f) ? 0 : flat + 1;
         f = ft;
         if (at_floor) { status = ST_CONVERGED; ++it; break; }
+        if (flat >= 3) { status = res <= (T)1000 * tol ? ST_CONVERGED : ST_STALLED; ++it; break; }
     }
     out.r = rc.raw(); out.iters = it; out.status = status;
 }

@@ -379,3 +379,22 @@ def test_tsp50_benchmark_regime_sample_matches_oracle():
     for precision in ("fp64", "fp32"):
         out = _run(pred, ctrs, mode=1, inner_ratio=0.2, reduction="none", precision=precision)
         _check(out, ref, RTOL[precision], 1)
+
+
+def test_newton_ends_at_the_floating_point_floor_of_a_degenerate_instance():
+    """SP 5x5, generator seed 1001, instance 3905, uniform predictions (tests/golden/regress/sp5_newton_floor.npz; found by
+    the two-GPU bench, whose rank 1 draws seed 1001): the float64 Newton iteration reaches the solution in 9 steps, then its
+    KKT residual hovers at 25 x tol while every further step is accepted with a length of 2^-24 and no change of the objective.
+    It used to run to the iteration cap (status ITER_CAP, 5 ms for one 90 x 40 instance); it must stop, converged, and match
+    the oracle."""
+    from cave_b200 import cave_forward_backward
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "regress", "sp5_newton_floor.npz"))
+    dev = torch.device("cuda:0")
+    A = torch.tensor(z["A"][None], device=dev)
+    pred = torch.tensor(z["pred"][None], device=dev)
+    for prec in ("fp64", "fp32"):
+        out = cave_forward_backward(pred, A, -1.0, 0, 0.0, "none", precision=prec, want_proj=True, want_status=True)
+        assert int(out["status"][0]) & 0xff == 0 and int(out["iters"][0]) <= 20, (prec, int(out["status"][0]), int(out["iters"][0]))
+        ref_p, ref_r = O.batch_project(-z["pred"][None].astype(np.float64), z["A"][None], fp64=True)
+        assert np.abs(out["proj"].double().cpu().numpy() - ref_p).max() <= 1e-6 * np.abs(ref_p).max()
+        np.testing.assert_allclose(out["rnorm"].double().cpu().numpy(), ref_r, rtol=1e-6)

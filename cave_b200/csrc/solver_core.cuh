@@ -1057,7 +1057,10 @@ CAVE_DEV void newton_solve(Ctx& cx, const Instance& in, Arena& ar, HPtr<TC, HOT>
         flat = (alpha > (T)0.0009765625 || ft < f - (T)16 * eps_mach<T>() * f) ? 0 : flat + 1;
         f = ft;
         if (at_floor) { status = ST_CONVERGED; ++it; break; }
-        if (flat >= 3) { status = res <= (T)1000 * tol ? ST_CONVERGED : ST_STALLED; ++it; break; }
+        if (flat >= 3) {    // (the residual is re-evaluated here rather than kept live through the iteration: two registers)
+            const T res_now = nw_grad(cx, W, rc, W.g, nu);
+            status = res_now <= (T)1000 * tol ? ST_CONVERGED : ST_STALLED; ++it; break;
+        }
     }
     out.r = rc.raw(); out.iters = it; out.status = status;
 }

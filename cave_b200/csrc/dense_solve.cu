@@ -486,16 +486,36 @@ __device__ void chol_solve_blocked(const float* __restrict__ W, int ldw, int nf,
             const int i = t / kNB, j = t - i * kNB;
             S.D[i * LD + j] = (i < nb && j <= i) ? W[(size_t)(j0 + i) * ldw + j0 + j] : (i == j ? 1.0f : 0.0f);
         }
-        for (int i = warp; i < nb; i += kDT / 32) {         // s_i = sum_{p < j0} L[i][p] y[p]
-            const float* row = W + (size_t)(j0 + i) * ldw;
-            float s = 0.0f;
+        {   // s_i = sum_{p < j0} L[i][p] y[p]: the four rows of a warp (i = warp + 16 t) together, so that their loads (from L2 /
+            // HBM) are in flight at once instead of one row after the other
+            const float* rows[4];
+            float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = warp + t * (kDT / 32);
+                rows[t] = W + (size_t)(j0 + (i < nb ? i : 0)) * ldw;
+            }
+#pragma unroll 2
             for (int q = lane * 4; q < j0; q += 128) {
-                const float4 l4 = *reinterpret_cast<const float4*>(row + q);
-                s = fmaf(l4.x, x[q], s); s = fmaf(l4.y, x[q + 1], s); s = fmaf(l4.z, x[q + 2], s); s = fmaf(l4.w, x[q + 3], s);
+                float4 l4[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) l4[t] = *reinterpret_cast<const float4*>(rows[t] + q);
+                const float x0 = x[q], x1 = x[q + 1], x2 = x[q + 2], x3 = x[q + 3];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    s[t] = fmaf(l4[t].x, x0, s[t]); s[t] = fmaf(l4[t].y, x1, s[t]);
+                    s[t] = fmaf(l4[t].z, x2, s[t]); s[t] = fmaf(l4[t].w, x3, s[t]);
+                }
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) S.invd[i] = s;
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], o);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) { const int i = warp + t * (kDT / 32); if (i < nb) S.invd[i] = s[t]; }
+            }
         }
         __syncthreads();
         if (warp == 0) {                                    // 64-step substitution, two rows per lane
@@ -522,11 +542,24 @@ __device__ void chol_solve_blocked(const float* __restrict__ W, int ldw, int nf,
         }
         // s_c = sum_{i >= j0 + nb} L[i][j0 + c] x[i]: warps over rows i, lanes over the block's columns (two each)
         float s0 = 0.0f, s1 = 0.0f;
-        for (int i = j0 + nb + warp; i < nf; i += kDT / 32) {
-            const float xi = x[i];
-            const float* row = W + (size_t)i * ldw + j0;
-            s0 = fmaf(row[lane], xi, s0);
-            s1 = fmaf(row[lane + 32], xi, s1);
+        {
+            int i = j0 + nb + warp;
+            for (; i + 7 * (kDT / 32) < nf; i += 8 * (kDT / 32)) {          // eight rows (sixteen loads) in flight per lane
+                float a0[8], a1[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float* row = W + (size_t)(i + u * (kDT / 32)) * ldw + j0;
+                    a0[u] = row[lane]; a1[u] = row[lane + 32];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const float xi = x[i + u * (kDT / 32)]; s0 = fmaf(a0[u], xi, s0); s1 = fmaf(a1[u], xi, s1); }
+            }
+            for (; i < nf; i += kDT / 32) {
+                const float xi = x[i];
+                const float* row = W + (size_t)i * ldw + j0;
+                s0 = fmaf(row[lane], xi, s0);
+                s1 = fmaf(row[lane + 32], xi, s1);
+            }
         }
         S.As[warp * kNB + lane] = s0; S.As[warp * kNB + lane + 32] = s1;
         __syncthreads();
